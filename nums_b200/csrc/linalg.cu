@@ -1,0 +1,391 @@
+// Dense factorisations of one block -- replaces np.linalg.qr / inv / cholesky / svd at
+// nums/core/systems/numpy_compute.py:240-257 (LAPACK geqrf, getrf+getri, potrf, gesdd in the
+// reference).
+//
+// QR (the TSQR leaf, application.py:784-814): a streaming Householder factorisation.  Every CTA
+// keeps the current n x n triangle R in shared memory and annihilates one chunk of rows after
+// another against it; annihilating column j of [R; chunk] only couples row j of R with the
+// chunk (R is upper triangular), so a step costs 2 c (n - j) FMA for a c-row chunk and the
+// whole leaf costs the textbook 2 m n^2.  The per-CTA triangles are then stacked and reduced by
+// the same kernel (a tree whose fan-in is 4) until one R is left.  This is the exact
+// Householder R of the block (up to row signs), backward stable for any conditioning.
+//
+// inv / cholesky: single-CTA in-place elimination in shared memory (global scratch beyond
+// ~160 x 160): the matrices on the path are the 28 x 28 LR Hessian and the 128 x 128 TSQR R,
+// so this is latency, not throughput.
+#include "common.cuh"
+
+namespace nums {
+namespace {
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// =====================================================================================
+// streaming Householder R
+// =====================================================================================
+constexpr int kQrThreads = 256;
+constexpr int kQrWarps = kQrThreads / 32;
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// CR = chunk rows per lane (chunk = 32 * CR rows).
+// A: row-major (m x n, pitch lda).  CTA b handles rows [b * rows_per_cta, (b+1) * rows_per_cta).
+// Rout: per-CTA dense n x n triangles (zeros below the diagonal), CTA b at Rout + b * n * n.
+template <typename T, int CR>
+__global__ void __launch_bounds__(kQrThreads, 1)
+tsqr_stream_kernel(const T* __restrict__ A, int64_t lda, int64_t m, int n, int64_t rows_per_cta,
+                   T* __restrict__ Rout, int64_t r_rows, int64_t ldr) {
+  extern __shared__ __align__(16) unsigned char qr_smem[];
+  T* R = reinterpret_cast<T*>(qr_smem);
+  const int pitch = n | 1;              // odd pitch: column walks are bank-conflict free
+  T* C = R + (size_t)n * pitch;         // chunk, 32*CR rows
+  constexpr int CH = 32 * CR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < n * pitch; i += kQrThreads) R[i] = T(0);
+
+  const int64_t row_lo = (int64_t)blockIdx.x * rows_per_cta;
+  int64_t row_hi = row_lo + rows_per_cta;
+  if (row_hi > m) row_hi = m;
+
+  for (int64_t base = row_lo; base < row_hi; base += CH) {
+    __syncthreads();
+    // coalesced load of the chunk, zero rows past the end
+    for (int e = threadIdx.x; e < CH * n; e += kQrThreads) {
+      const int i = e / n, c = e - i * n;
+      const int64_t gr = base + i;
+      C[i * pitch + c] = gr < row_hi ? A[gr * lda + c] : T(0);
+    }
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+      // Householder vector for column j of [R(j,j); chunk(:, j)] (LAPACK dlarfg), computed
+      // redundantly by every warp so no broadcast is needed.
+      T v[CR];
+      T sigma = T(0);
+#pragma unroll
+      for (int r = 0; r < CR; ++r) {
+        v[r] = C[(lane + 32 * r) * pitch + j];
+        sigma += v[r] * v[r];
+      }
+      sigma = warp_sum(sigma);
+      const T alpha = R[j * pitch + j];
+      T tau = T(0), beta = alpha;
+      if (sigma != T(0)) {
+        const T nrm = sqrt(alpha * alpha + sigma);
+        beta = alpha >= T(0) ? -nrm : nrm;
+        tau = (beta - alpha) / beta;
+        const T scale = T(1) / (alpha - beta);
+#pragma unroll
+        for (int r = 0; r < CR; ++r) v[r] *= scale;
+      }
+      if (tau != T(0)) {
+        // apply H = I - tau [1; v][1; v]^T to the trailing columns, 2 columns per warp in flight
+        int c = j + 1 + warp;
+        for (; c + kQrWarps < n; c += 2 * kQrWarps) {
+          const int c2 = c + kQrWarps;
+          T w0 = T(0), w1 = T(0);
+          T x0[CR], x1[CR];
+#pragma unroll
+          for (int r = 0; r < CR; ++r) {
+            x0[r] = C[(lane + 32 * r) * pitch + c];
+            x1[r] = C[(lane + 32 * r) * pitch + c2];
+            w0 += v[r] * x0[r];
+            w1 += v[r] * x1[r];
+          }
+          w0 = warp_sum(w0);
+          w1 = warp_sum(w1);
+          const T r0 = R[j * pitch + c], r1 = R[j * pitch + c2];
+          const T t0 = tau * (w0 + r0), t1 = tau * (w1 + r1);
+#pragma unroll
+          for (int r = 0; r < CR; ++r) {
+            C[(lane + 32 * r) * pitch + c] = x0[r] - t0 * v[r];
+            C[(lane + 32 * r) * pitch + c2] = x1[r] - t1 * v[r];
+          }
+          if (lane == 0) {
+            R[j * pitch + c] = r0 - t0;
+            R[j * pitch + c2] = r1 - t1;
+          }
+        }
+        if (c < n) {
+          T w0 = T(0);
+          T x0[CR];
+#pragma unroll
+          for (int r = 0; r < CR; ++r) {
+            x0[r] = C[(lane + 32 * r) * pitch + c];
+            w0 += v[r] * x0[r];
+          }
+          w0 = warp_sum(w0);
+          const T r0 = R[j * pitch + c];
+          const T t0 = tau * (w0 + r0);
+#pragma unroll
+          for (int r = 0; r < CR; ++r) C[(lane + 32 * r) * pitch + c] = x0[r] - t0 * v[r];
+          if (lane == 0) R[j * pitch + c] = r0 - t0;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) R[j * pitch + j] = beta;
+    }
+  }
+  __syncthreads();
+  T* out = Rout + (size_t)blockIdx.x * r_rows * ldr;
+  for (int e = threadIdx.x; e < (int)r_rows * n; e += kQrThreads) {
+    const int i = e / n, c = e - i * n;
+    out[(size_t)i * ldr + c] = (c >= i) ? R[i * pitch + c] : T(0);
+  }
+}
+
+template <typename T, int CR>
+int launch_tsqr(const T* A, int64_t lda, int64_t m, int n, int64_t rows_per_cta, int ctas, T* Rout,
+                int64_t r_rows, int64_t ldr, cudaStream_t s) {
+  const size_t smem = (size_t)(n + 32 * CR) * (n | 1) * sizeof(T);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(tsqr_stream_kernel<T, CR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tsqr_stream_kernel<T, CR><<<ctas, kQrThreads, smem, s>>>(A, lda, m, n, rows_per_cta, Rout, r_rows, ldr);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
+template <typename T>
+int launch_tsqr_auto(const T* A, int64_t lda, int64_t m, int n, int64_t rows_per_cta, int ctas, T* Rout,
+                     int64_t r_rows, int64_t ldr, cudaStream_t s) {
+  const size_t budget = 200 * 1024;
+  const size_t row_bytes = (size_t)(n | 1) * sizeof(T);
+  if ((size_t)(n + 128) * row_bytes <= budget) return launch_tsqr<T, 4>(A, lda, m, n, rows_per_cta, ctas, Rout, r_rows, ldr, s);
+  if ((size_t)(n + 64) * row_bytes <= budget) return launch_tsqr<T, 2>(A, lda, m, n, rows_per_cta, ctas, Rout, r_rows, ldr, s);
+  if ((size_t)(n + 32) * row_bytes <= 227 * 1024) return launch_tsqr<T, 1>(A, lda, m, n, rows_per_cta, ctas, Rout, r_rows, ldr, s);
+  NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "qr: %d columns do not fit the shared-memory TSQR leaf", n);
+}
+
+template <typename T>
+int run_qr_r(int64_t m, int64_t n64, const T* A, int64_t lda, T* R, int64_t ldr, void* ws, size_t ws_bytes,
+             cudaStream_t s) {
+  const int n = (int)n64;
+  const int64_t k = m < n ? m : n;
+  // Leaf: at least 4n rows per CTA (so the leaf dominates the merges), at most one CTA per SM.
+  int64_t min_rows = 4 * (int64_t)n;
+  if (min_rows < 256) min_rows = 256;
+  int64_t ctas = ceil_div(m, min_rows);
+  if (ctas > sm_count()) ctas = sm_count();
+  if (ctas < 1) ctas = 1;
+  int64_t rows_per_cta = ceil_div(m, ctas);
+  ctas = ceil_div(m, rows_per_cta);
+  if (ctas == 1) return launch_tsqr_auto<T>(A, lda, m, n, rows_per_cta, 1, R, k, ldr, s);
+  // ping-pong buffers of stacked n x n triangles
+  const size_t level0 = (size_t)ctas * n * n * sizeof(T);
+  const size_t level1 = (size_t)ceil_div(ctas, 4) * n * n * sizeof(T);
+  const size_t off1 = (level0 + 255) & ~(size_t)255;
+  NUMS_NEED_WS(off1 + level1, ws_bytes);
+  T* buf0 = static_cast<T*>(ws);
+  T* buf1 = reinterpret_cast<T*>(static_cast<char*>(ws) + off1);
+  if (int rc = launch_tsqr_auto<T>(A, lda, m, n, rows_per_cta, (int)ctas, buf0, n, n, s)) return rc;
+  T* src = buf0;
+  T* dst = buf1;
+  int64_t count = ctas;
+  while (count > 1) {
+    const int64_t next = ceil_div(count, 4);
+    const int64_t rows = count * n;
+    if (next == 1) return launch_tsqr_auto<T>(src, n, rows, n, rows, 1, R, k, ldr, s);
+    if (int rc = launch_tsqr_auto<T>(src, n, rows, n, 4 * (int64_t)n, (int)next, dst, n, n, s)) return rc;
+    T* tmp = src;
+    src = dst;
+    dst = tmp;
+    count = next;
+  }
+  return NUMS_OK;
+}
+
+// =====================================================================================
+// inverse (Gauss-Jordan, partial pivoting) and Cholesky, one CTA
+// =====================================================================================
+constexpr int kLaThreads = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(kLaThreads, 1)
+inv_kernel(const T* __restrict__ A, int64_t lda, int n, T* __restrict__ out, int64_t ldo, T* scratch,
+           int use_smem, int32_t* info) {
+  extern __shared__ __align__(16) unsigned char la_smem[];
+  const int pitch = use_smem ? (n | 1) : n;
+  T* M = use_smem ? reinterpret_cast<T*>(la_smem) : scratch;
+  __shared__ int piv_row;
+  __shared__ int perm[1024];
+  __shared__ T colk[1024];
+  __shared__ int failed;
+  const int tid = threadIdx.x;
+  if (tid == 0) failed = 0;
+  for (int e = tid; e < n * n; e += kLaThreads) {
+    const int i = e / n, c = e - i * n;
+    M[i * pitch + c] = A[(int64_t)i * lda + c];
+  }
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    // pivot search by warp 0: first maximum of |M[i][k]|, i >= k
+    if (tid < 32) {
+      T best = T(-1);
+      int bi = k;
+      for (int i = k + tid; i < n; i += 32) {
+        const T a = fabs(M[i * pitch + k]);
+        if (a > best) {
+          best = a;
+          bi = i;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const T ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+          best = ob;
+          bi = oi;
+        }
+      }
+      if (tid == 0) {
+        piv_row = bi;
+        perm[k] = bi;
+        if (!(best > T(0)) && failed == 0) failed = k + 1;
+      }
+    }
+    __syncthreads();
+    const int p = piv_row;
+    if (p != k) {
+      for (int c = tid; c < n; c += kLaThreads) {
+        const T a = M[k * pitch + c];
+        M[k * pitch + c] = M[p * pitch + c];
+        M[p * pitch + c] = a;
+      }
+    }
+    __syncthreads();
+    const T pivot = M[k * pitch + k];
+    const T rp = T(1) / pivot;
+    // save column k, then overwrite it with the unit column (in-place inversion)
+    for (int i = tid; i < n; i += kLaThreads) colk[i] = M[i * pitch + k];
+    __syncthreads();
+    for (int i = tid; i < n; i += kLaThreads) M[i * pitch + k] = (i == k) ? T(1) : T(0);
+    __syncthreads();
+    for (int c = tid; c < n; c += kLaThreads) M[k * pitch + c] *= rp;
+    __syncthreads();
+    for (int e = tid; e < n * n; e += kLaThreads) {
+      const int i = e / n, c = e - i * n;
+      if (i != k) M[i * pitch + c] -= colk[i] * M[k * pitch + c];
+    }
+    __syncthreads();
+  }
+  // undo the row interchanges as column interchanges, in reverse order
+  for (int k = n - 1; k >= 0; --k) {
+    const int p = perm[k];
+    if (p != k) {
+      for (int i = tid; i < n; i += kLaThreads) {
+        const T a = M[i * pitch + k];
+        M[i * pitch + k] = M[i * pitch + p];
+        M[i * pitch + p] = a;
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < n * n; e += kLaThreads) {
+    const int i = e / n, c = e - i * n;
+    out[(int64_t)i * ldo + c] = M[i * pitch + c];
+  }
+  if (tid == 0 && info != nullptr) *info = failed;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLaThreads, 1)
+cholesky_kernel(const T* __restrict__ A, int64_t lda, int n, T* __restrict__ out, int64_t ldo, T* scratch,
+                int use_smem, int32_t* info) {
+  extern __shared__ __align__(16) unsigned char la_smem[];
+  const int pitch = use_smem ? (n | 1) : n;
+  T* M = use_smem ? reinterpret_cast<T*>(la_smem) : scratch;
+  __shared__ int failed;
+  const int tid = threadIdx.x;
+  if (tid == 0) failed = 0;
+  for (int e = tid; e < n * n; e += kLaThreads) {
+    const int i = e / n, c = e - i * n;
+    M[i * pitch + c] = A[(int64_t)i * lda + c];
+  }
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    const T dkk = M[k * pitch + k];
+    if (!(dkk > T(0))) {
+      if (tid == 0 && failed == 0) failed = k + 1;
+    }
+    const T l = sqrt(dkk);
+    __syncthreads();
+    for (int i = k + tid; i < n; i += kLaThreads) M[i * pitch + k] = (i == k) ? l : M[i * pitch + k] / l;
+    __syncthreads();
+    const int rem = n - k - 1;
+    for (int e = tid; e < rem * rem; e += kLaThreads) {
+      const int i = k + 1 + e / rem, c = k + 1 + e % rem;
+      if (c <= i) M[i * pitch + c] -= M[i * pitch + k] * M[c * pitch + k];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < n * n; e += kLaThreads) {
+    const int i = e / n, c = e - i * n;
+    out[(int64_t)i * ldo + c] = (c <= i) ? M[i * pitch + c] : T(0);
+  }
+  if (tid == 0 && info != nullptr) *info = failed;
+}
+
+template <typename T, typename K>
+int run_single_cta(K kernel, int64_t n, const T* A, int64_t lda, T* out, int64_t ldo, int32_t* info, void* ws,
+                   size_t ws_bytes, cudaStream_t s, const char* what) {
+  NUMS_REQUIRE(n >= 1 && n <= 1024, "%s: n = %lld outside the supported range [1, 1024]", what, (long long)n);
+  const size_t smem = (size_t)n * (n | 1) * sizeof(T);
+  const bool use_smem = smem <= 200 * 1024;
+  if (!use_smem) NUMS_NEED_WS((size_t)n * n * sizeof(T), ws_bytes);
+  if (use_smem) NUMS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kernel<<<1, kLaThreads, use_smem ? smem : 0, s>>>(A, lda, (int)n, out, ldo, static_cast<T*>(ws), use_smem ? 1 : 0, info);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
+}  // namespace
+}  // namespace nums
+
+extern "C" int nums_qr(int dtype, int64_t m, int64_t n, const void* A, int64_t lda, void* Q, int64_t ldq,
+                       void* R, int64_t ldr, void* ws, size_t ws_bytes, void* stream) {
+  using namespace nums;
+  (void)ldq;
+  NUMS_REQUIRE(m >= 1 && n >= 1, "qr: empty matrix");
+  NUMS_REQUIRE(A && R, "qr: null pointer");
+  if (Q != nullptr)
+    NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "qr: explicit Q is formed by the caller as A R^-1 (+ one refinement)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == NUMS_F64) return run_qr_r<double>(m, n, static_cast<const double*>(A), lda, static_cast<double*>(R), ldr, ws, ws_bytes, s);
+  if (dtype == NUMS_F32) return run_qr_r<float>(m, n, static_cast<const float*>(A), lda, static_cast<float*>(R), ldr, ws, ws_bytes, s);
+  NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "qr: dtype %s", dtype_name(dtype));
+}
+
+extern "C" int nums_inv(int dtype, int64_t n, const void* A, int64_t lda, void* Ainv, int64_t ldi,
+                        int32_t* info, void* ws, size_t ws_bytes, void* stream) {
+  using namespace nums;
+  NUMS_REQUIRE(A && Ainv, "inv: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == NUMS_F64)
+    return run_single_cta<double>(inv_kernel<double>, n, static_cast<const double*>(A), lda, static_cast<double*>(Ainv), ldi, info, ws, ws_bytes, s, "inv");
+  if (dtype == NUMS_F32)
+    return run_single_cta<float>(inv_kernel<float>, n, static_cast<const float*>(A), lda, static_cast<float*>(Ainv), ldi, info, ws, ws_bytes, s, "inv");
+  NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "inv: dtype %s", dtype_name(dtype));
+}
+
+extern "C" int nums_cholesky(int dtype, int64_t n, const void* A, int64_t lda, void* L, int64_t ldl,
+                             int32_t* info, void* ws, size_t ws_bytes, void* stream) {
+  using namespace nums;
+  NUMS_REQUIRE(A && L, "cholesky: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == NUMS_F64)
+    return run_single_cta<double>(cholesky_kernel<double>, n, static_cast<const double*>(A), lda, static_cast<double*>(L), ldl, info, ws, ws_bytes, s, "cholesky");
+  if (dtype == NUMS_F32)
+    return run_single_cta<float>(cholesky_kernel<float>, n, static_cast<const float*>(A), lda, static_cast<float*>(L), ldl, info, ws, ws_bytes, s, "cholesky");
+  NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "cholesky: dtype %s", dtype_name(dtype));
+}
+
+extern "C" int nums_svd(int dtype, int64_t n, const void* A, int64_t lda, void* U, void* S, void* Vt,
+                        void* ws, size_t ws_bytes, void* stream) {
+  using namespace nums;
+  (void)dtype; (void)n; (void)A; (void)lda; (void)U; (void)S; (void)Vt; (void)ws; (void)ws_bytes; (void)stream;
+  NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "svd: not implemented yet in this build");
+}

@@ -1,0 +1,256 @@
+// Fused logistic-regression gradient + Hessian over one row block.
+//
+// The reference composes this from ~15 per-block kernel calls per Newton iteration
+// (nums/models/glms.py:140-143 forward, :213-214 link_inv, :222-227 gradient, :232-238
+// hessian; call trace in SURVEY.md 3.5): X is streamed about six times and an X-sized
+// temporary `s * X` is materialised.  Here one pass over X produces
+//     g = X^T (mu - y),   H = X^T diag(mu (1 - mu)) X,   mu = 1 / (1 + exp(-X beta)).
+//
+// Layout / roofline: X (n x d, row-major f64) is read exactly once, 8 n (d + 1) bytes.  With
+// d = 28 the Hessian needs d(d+1)/2 = 406 FMA per 232 bytes, about the FP64 ridge of a B200,
+// so the rank-k update runs on the FP64 tensor pipe (DMMA m8n8k4, only the upper-triangular
+// 8x8 blocks), the dot products X beta and the gradient ride along in the same fragment
+// layout, and exp() is evaluated once per row (not once per fragment lane).
+//
+// Each CTA is persistent (grid = #SMs), stages 256-row tiles through a cp.async ring and
+// writes one partial (g | H) to the workspace; a second tiny kernel folds the partials in a
+// fixed order (deterministic, no atomics) and mirrors H.
+#include "common.cuh"
+
+namespace nums {
+namespace {
+
+constexpr int kLrThreads = 256;
+constexpr int kTileRows = 256;  // 8 warps x 32 rows
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// pitch == 4 (mod 16) doubles => the (row = t, feature = g) fragment reads are conflict free
+__host__ __device__ constexpr int lr_pitch(int nb) { return ((nb * 8 + 11) / 16) * 16 + 4; }
+
+template <int NB>  // NB = ceil(d / 8) feature blocks
+__global__ void __launch_bounds__(kLrThreads, 1)
+lr_grad_hess_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ y,
+                    const double* __restrict__ beta, int64_t n, int d, int stages,
+                    double* __restrict__ partial) {
+  constexpr int PITCH = lr_pitch(NB);
+  constexpr int NTRI = NB * (NB + 1) / 2;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int chunks_per_row = d / 2;  // d is even (checked on the host)
+
+  // zero the whole ring once: padding columns are never written by cp.async afterwards
+  for (int i = threadIdx.x; i < stages * kTileRows * PITCH; i += kLrThreads) smem[i] = 0.0;
+  __syncthreads();
+
+  double bfrag[NB];  // beta[8 bi + g]
+#pragma unroll
+  for (int bi = 0; bi < NB; ++bi) bfrag[bi] = (8 * bi + g < d) ? beta[8 * bi + g] : 0.0;
+
+  double hacc[NTRI][2];
+  double gacc[NB];
+#pragma unroll
+  for (int i = 0; i < NTRI; ++i) hacc[i][0] = hacc[i][1] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) gacc[i] = 0.0;
+
+  const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
+  auto load_tile = [&](int slot, int64_t tile) {
+    double* dst = smem + (size_t)slot * kTileRows * PITCH;
+    const int64_t r0 = tile * kTileRows;
+    const int total = kTileRows * chunks_per_row;
+    for (int c = threadIdx.x; c < total; c += kLrThreads) {
+      const int r = c / chunks_per_row, cc = (c - r * chunks_per_row) * 2;
+      const int64_t gr = r0 + r;
+      const bool in = gr < n;
+      cp_async16(dst + r * PITCH + cc, in ? X + gr * ldx + cc : X, in ? 16 : 0);
+    }
+  };
+
+  int64_t tile = blockIdx.x;
+  // prologue: prefetch stages-1 tiles
+  for (int s = 0; s < stages - 1; ++s) {
+    const int64_t tl = tile + (int64_t)s * gridDim.x;
+    if (tl < ntiles) load_tile(s, tl);
+    cp_async_commit();
+  }
+  int slot = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    if (stages == 3) cp_async_wait<1>();
+    else cp_async_wait<0>();
+    __syncthreads();
+    {
+      const int64_t nxt = tile + (int64_t)(stages - 1) * gridDim.x;
+      int nslot = slot + stages - 1;
+      if (nslot >= stages) nslot -= stages;
+      if (nxt < ntiles) load_tile(nslot, nxt);
+      cp_async_commit();
+    }
+    const double* xs = smem + (size_t)slot * kTileRows * PITCH + (size_t)warp * 32 * PITCH;
+    const int64_t row0 = tile * kTileRows + warp * 32;
+
+    // pass 1: z for the warp's 32 rows.  After the reduction every lane with the same t holds
+    // z[4 q + t] for group q; lane (g, t) keeps the one with q == g, i.e. row 4 g + t.
+    double zmine = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const double* xr = xs + (4 * q + t) * PITCH + g;
+      double z = 0.0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi) z = fma(xr[8 * bi], bfrag[bi], z);
+      z += __shfl_xor_sync(0xffffffffu, z, 4);
+      z += __shfl_xor_sync(0xffffffffu, z, 8);
+      z += __shfl_xor_sync(0xffffffffu, z, 16);
+      if (q == g) zmine = z;
+    }
+    const int64_t myrow = row0 + 4 * g + t;
+    const double yv = myrow < n ? y[myrow] : 0.0;
+    const double mu = 1.0 / (1.0 + exp(-zmine));
+    const double e_mine = mu - yv;
+    const double s_mine = mu * (1.0 - mu);
+
+    // pass 2: rank-4 updates per group.
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const double s = __shfl_sync(0xffffffffu, s_mine, 4 * q + t);
+      const double e = __shfl_sync(0xffffffffu, e_mine, 4 * q + t);
+      const double* xr = xs + (4 * q + t) * PITCH + g;
+      double xf[NB], af[NB];
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi) {
+        xf[bi] = xr[8 * bi];
+        af[bi] = s * xf[bi];
+        gacc[bi] = fma(e, xf[bi], gacc[bi]);
+      }
+      int idx = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj) {
+          dmma884(hacc[idx], af[bi], xf[bj]);
+          ++idx;
+        }
+    }
+    ++slot;
+    if (slot == stages) slot = 0;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- CTA fold through shared memory (reuses the ring) ----------------------------------------
+  // layout per warp: [NB*8 gradient][ (NB*8)^2 hessian ]
+  constexpr int D8 = NB * 8;
+  constexpr int PER_WARP = D8 + D8 * D8;
+  double* red = smem;  // 8 * PER_WARP doubles <= ring size (checked on the host)
+  for (int i = threadIdx.x; i < 8 * PER_WARP; i += kLrThreads) red[i] = 0.0;
+  __syncthreads();
+  double* mine = red + warp * PER_WARP;
+#pragma unroll
+  for (int bi = 0; bi < NB; ++bi) {
+    double v = gacc[bi];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (t == 0) mine[8 * bi + g] = v;
+  }
+  {
+    int idx = 0;
+#pragma unroll
+    for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+      for (int bj = bi; bj < NB; ++bj) {
+        double* h = mine + D8 + (8 * bi + g) * D8 + 8 * bj + 2 * t;
+        h[0] = hacc[idx][0];
+        h[1] = hacc[idx][1];
+        ++idx;
+      }
+  }
+  __syncthreads();
+  double* out = partial + (size_t)blockIdx.x * (d + d * d);
+  for (int i = threadIdx.x; i < d + d * d; i += kLrThreads) {
+    int src;
+    if (i < d) src = i;
+    else {
+      const int r = (i - d) / d, c = (i - d) - r * d;
+      // blocks below the block diagonal were not computed: read the mirrored entry
+      src = (r / 8 <= c / 8) ? D8 + r * D8 + c : D8 + c * D8 + r;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc += red[w * PER_WARP + src];
+    out[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lr_fold_kernel(const double* __restrict__ partial, int parts, int len, double* __restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= len) return;
+  double acc = 0.0;
+  for (int p = 0; p < parts; ++p) acc += partial[(size_t)p * len + i];
+  out[i] = acc;
+}
+
+template <int NB>
+int launch_lr(const double* X, int64_t ldx, const double* y, const double* beta, int64_t n, int d,
+              double* out, void* ws, size_t ws_bytes, cudaStream_t s) {
+  constexpr int PITCH = lr_pitch(NB);
+  const size_t stage_bytes = (size_t)kTileRows * PITCH * sizeof(double);
+  int stages = 3;
+  if (3 * stage_bytes > 220 * 1024) stages = 2;
+  const size_t smem = stages * stage_bytes;
+  NUMS_REQUIRE(smem <= 227 * 1024, "lr_grad_hess: d = %d needs too much shared memory", d);
+  NUMS_REQUIRE((size_t)8 * (NB * 8 + NB * 8 * NB * 8) * sizeof(double) <= smem,
+               "lr_grad_hess: reduction scratch does not fit");
+  const int len = d + d * d;
+  const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
+  int grid = sm_count();
+  if (grid > ntiles) grid = (int)ntiles;
+  if (grid < 1) grid = 1;
+  NUMS_NEED_WS((size_t)grid * len * sizeof(double), ws_bytes);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(lr_grad_hess_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lr_grad_hess_kernel<NB><<<grid, kLrThreads, smem, s>>>(X, ldx, y, beta, n, d, stages, static_cast<double*>(ws));
+  NUMS_LAUNCH_OK();
+  lr_fold_kernel<<<(len + 255) / 256, 256, 0, s>>>(static_cast<const double*>(ws), grid, len, out);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
+}  // namespace
+}  // namespace nums
+
+extern "C" int nums_lr_grad_hess(int64_t n, int64_t d, const double* X, int64_t ldx, const double* y,
+                                 const double* beta, double* out, void* ws, size_t ws_bytes,
+                                 void* stream) {
+  using namespace nums;
+  NUMS_REQUIRE(n >= 1 && d >= 1, "lr_grad_hess: empty block");
+  NUMS_REQUIRE(X && y && beta && out, "lr_grad_hess: null pointer");
+  if (d > 64 || d % 2 != 0 || ldx % 2 != 0 || (reinterpret_cast<uintptr_t>(X) & 15u) != 0)
+    NUMS_FAIL(NUMS_ERR_UNSUPPORTED,
+              "lr_grad_hess: needs even d <= 64, even row pitch and a 16-byte aligned X (d=%lld, ldx=%lld)",
+              (long long)d, (long long)ldx);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch ((d + 7) / 8) {
+    case 1: return launch_lr<1>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
+    case 2: return launch_lr<2>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
+    case 3: return launch_lr<3>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
+    case 4: return launch_lr<4>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
+    case 5: return launch_lr<5>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
+    case 6: return launch_lr<6>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
+    case 7: return launch_lr<7>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
+    case 8: return launch_lr<8>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
+  }
+  NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "lr_grad_hess: d = %lld", (long long)d);
+}

@@ -1,0 +1,666 @@
+"""``cuda_compute`` -- the B200 implementation of NumS' per-block compute interface.
+
+Drop-in beside ``nums.core.systems.numpy_compute``: this module exports ``ComputeCls`` (the 28
+methods of ``ComputeInterface``, /root/reference/nums/core/systems/interfaces.py:73-167, with
+the parameter names ``check_implementation`` compares, systems/utils.py:59-72) and ``RNG``
+(numpy_compute.py:33-81).  Blocks ("oids") are ``torch.Tensor`` objects living in HBM; every
+method enqueues hand-written sm_100a kernels from ``libnumscuda.so`` (C ABI in
+``include/nums_cuda.h``) on the current CUDA stream and returns immediately -- the only
+synchronisation points are ``touch`` and the host reads documented below.  PyTorch is used for
+device memory, views (metadata) and streams only.
+
+There is no CPU fallback: anything the kernel library does not implement raises
+``NotImplementedError``; a missing ``libnumscuda.so`` raises on first use.
+"""
+import random
+
+import numpy as np
+import scipy.special
+import torch
+
+from nums_b200 import _lib
+from nums_b200._lib import LIB, describe
+from nums_b200.grid import ArrayGrid
+
+try:  # when the reference package is importable, be a real ComputeImp / RNGInterface subclass
+    from nums.core.systems.interfaces import ComputeImp as _ComputeImp, RNGInterface as _RNGInterface
+except Exception:  # the GPU box has no reference tree
+    class _ComputeImp(object):
+        pass
+
+    class _RNGInterface(object):
+        pass
+
+# nums/core/settings.py:48-61 -- BlockArray operator names -> NumPy ufunc names
+_SHORT_OP_NAMES = {
+    "truediv": "true_divide", "sub": "subtract", "pow": "power", "mult": "multiply",
+    "mul": "multiply", "lt": "less", "le": "less_equal", "gt": "greater", "ge": "greater_equal",
+    "eq": "equal", "ne": "not_equal", "divide": "true_divide", "mod": "remainder",
+}
+
+# Whether inv/cholesky read back the pivot status (one 4-byte D2H sync) to raise LinAlgError
+# like NumPy does.  On by default: same error behaviour as the reference.
+CHECK_FACTORIZATION_STATUS = True
+
+
+class RNG(_RNGInterface):
+    """Same hand-out of (seed, jump_index) pairs as the reference (numpy_compute.py:70-81).
+
+    Sampling itself stays on the host with NumPy's PCG64 so that seeded streams are bit-identical
+    to the reference (tests/core/array/test_random.py:164-172); blocks are then uploaded.
+    """
+
+    def __init__(self, seed=None, jump_index=0):
+        if seed is None:
+            seed = random.getrandbits(128)
+        self.seed = seed
+        self.rng = np.random.PCG64(seed)
+        self.jump_index = jump_index
+
+    def new_block_rng_params(self):
+        params = self.seed, self.jump_index
+        self.jump_index += 1
+        return params
+
+
+def block_rng(seed, jump_index):
+    return np.random.Generator(np.random.PCG64(seed).jumped(jump_index))
+
+
+# ---------------------------------------------------------------------------------------------
+# plumbing helpers (metadata + allocation only)
+# ---------------------------------------------------------------------------------------------
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.NumsCudaError("cuda_compute needs a CUDA device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _empty(shape, dtype):
+    return torch.empty(tuple(int(s) for s in shape), dtype=_lib.torch_dtype(dtype), device=_device())
+
+
+def upload(value, dtype=None):
+    """Host value -> device tensor (pinned staging, async H2D on the current stream)."""
+    if isinstance(value, torch.Tensor):
+        return value
+    arr = np.asarray(value) if dtype is None else np.asarray(value, dtype=dtype)
+    _lib.dtype_code(arr.dtype)  # raises for unsupported dtypes
+    if not arr.flags.c_contiguous:
+        arr = np.ascontiguousarray(arr)
+    host = torch.from_numpy(arr.reshape(-1).copy() if arr.ndim == 0 else arr)
+    if host.numel() >= 1 << 16:
+        staged = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
+        staged.copy_(host)
+        out = staged.to(_device(), non_blocking=True)
+    else:
+        out = host.to(_device())
+    return out.view(tuple(arr.shape))
+
+
+def download(t):
+    """Device tensor -> numpy array (synchronises the current stream)."""
+    if not isinstance(t, torch.Tensor):
+        return t
+    if not t.is_contiguous():
+        t = _materialize(t)
+    return t.cpu().numpy()
+
+
+def _copy_into(dst, src):
+    """dst[...] = src with NumPy broadcasting and dtype conversion (nums_uop COPY)."""
+    if dst.numel() == 0:
+        return
+    LIB.check(LIB.dll.nums_uop(_lib.UOP_CODE["copy"], _lib.dtype_code(dst.dtype), describe(src),
+                               describe(dst), _stream()))
+
+
+def _materialize(view, dtype=None):
+    out = torch.empty(tuple(view.shape), dtype=view.dtype if dtype is None else dtype, device=view.device)
+    _copy_into(out, view)
+    return out
+
+
+def _transpose_view(t):
+    return t.permute(*reversed(range(t.dim()))) if t.dim() > 1 else t
+
+
+def _reshape(t, shape):
+    shape = tuple(int(s) for s in shape)
+    if tuple(t.shape) == shape:
+        return t
+    try:
+        return t.view(shape)
+    except RuntimeError:
+        return _materialize(t).view(shape)
+
+
+def _operand(a, shape, transposed):
+    """numpy_compute.py:222-229: `.T` if flagged, then reshape if the stored shape differs."""
+    a = upload(a)
+    if transposed:
+        a = _transpose_view(a)
+    if tuple(a.shape) != tuple(shape):
+        a = _reshape(a, shape)
+    return a
+
+
+def _np_dtype(name):
+    if isinstance(name, str):
+        return np.dtype({"int": np.int64, "float": np.float64, "bool": np.bool_}.get(name) or getattr(np, name))
+    return np.dtype(name)
+
+
+_BOP_TYPES = {}
+_UOP_TYPES = {}
+
+
+def _ufunc(name):
+    fn = getattr(np, name, None)
+    if fn is None:
+        fn = getattr(scipy.special, name)  # numpy_compute.py:234-238
+    return fn
+
+
+def bop_types(name, dt_a, dt_b):
+    """(loop dtype, output dtype) NumPy's type resolution picks for ufunc(name) on these inputs."""
+    key = (name, dt_a, dt_b)
+    hit = _BOP_TYPES.get(key)
+    if hit is None:
+        in_a, _in_b, out = _ufunc(name).resolve_dtypes((dt_a, dt_b, None))
+        hit = (np.dtype(in_a), np.dtype(out))
+        _BOP_TYPES[key] = hit
+    return hit
+
+
+def uop_types(name, dt):
+    key = (name, dt)
+    hit = _UOP_TYPES.get(key)
+    if hit is None:
+        in_a, out = _ufunc(name).resolve_dtypes((dt, None))
+        hit = (np.dtype(in_a), np.dtype(out))
+        _UOP_TYPES[key] = hit
+    return hit
+
+
+def _apply_sel(t, sel):
+    """Basic (slice / int) indexing as a view; mirrors ndarray[sel] for the selections
+    ArrayView generates (view.py:170-178, :358-365)."""
+    if sel is None:
+        return t
+    if not isinstance(sel, tuple):
+        sel = (sel,)
+    for s in sel:
+        if isinstance(s, slice) and s.step is not None and s.step < 0:
+            raise NotImplementedError("negative-step slices are not supported by cuda_compute")
+    return t[sel]
+
+
+class ComputeCls(_ComputeImp):
+    # ------------------------------------------------------------------ I/O-ish
+    def touch(self, arr):
+        """Synchronisation point (numpy_compute.py:88-89)."""
+        torch.cuda.current_stream().synchronize()
+        return isinstance(arr, torch.Tensor)
+
+    def empty(self, grid_entry, grid_meta):
+        grid = ArrayGrid.from_meta(grid_meta)
+        return _empty(grid.get_block_shape(grid_entry), grid.dtype)
+
+    def new_block(self, op_name, grid_entry, grid_meta):
+        grid = ArrayGrid.from_meta(grid_meta)
+        shape = grid.get_block_shape(grid_entry)
+        out = _empty(shape, grid.dtype)
+        if op_name == "eye":
+            assert np.all(np.diff(grid_entry) == 0)
+            if out.numel():
+                LIB.check(LIB.dll.nums_eye(describe(out), _stream()))
+        elif op_name in ("zeros", "ones"):
+            if out.numel():
+                LIB.check(LIB.dll.nums_fill(describe(out), 1.0 if op_name == "ones" else 0.0, _stream()))
+        elif op_name != "empty":
+            raise NotImplementedError("new_block(%s)" % op_name)
+        return out
+
+    def random_block(self, rng_params, rfunc_name, rfunc_args, shape, dtype):
+        rng = block_rng(*rng_params)
+        result = getattr(rng, rfunc_name)(*rfunc_args).reshape(shape)
+        if rfunc_name not in ("random", "integers"):
+            result = result.astype(dtype)
+        return upload(result)
+
+    def permutation(self, rng_params, size):
+        return upload(block_rng(*rng_params).permutation(size))
+
+    def diag(self, arr):
+        arr = upload(arr)
+        if arr.dim() == 1:
+            n = arr.shape[0]
+            out = _empty((n, n), arr.dtype)
+            if n:
+                LIB.check(LIB.dll.nums_fill(describe(out), 0.0, _stream()))
+                _copy_into(out.as_strided((n,), (n + 1,)), arr)
+            return out
+        if arr.dim() == 2:
+            k = min(arr.shape)
+            src = arr.as_strided((k,), (arr.stride(0) + arr.stride(1),), arr.storage_offset())
+            return _materialize(src)
+        raise ValueError("Input must be 1- or 2-d.")
+
+    def arange(self, start, stop, step, dtype):
+        ref = np.arange(0, 1, 1, dtype)  # dtype resolution as NumPy does it
+        length = int(max(0, np.ceil((stop - start) / step)))
+        out = _empty((length,), ref.dtype)
+        if length:
+            LIB.check(LIB.dll.nums_arange(describe(out), float(start), float(step), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ data movement
+    def create_block(self, *src_arrs, src_params, dst_params, dst_shape, dst_shape_bc):
+        first = upload(src_arrs[0])
+        result = _empty(dst_shape, first.dtype)
+        assert len(src_params) == len(dst_params)
+        target = result if dst_shape_bc is None else result.view(tuple(dst_shape_bc))
+        for i in range(len(src_params)):
+            src = upload(src_arrs[i])
+            src_sel, src_t = src_params[i]
+            if src_t:
+                src = _transpose_view(src)
+            dst_sel, _dst_t = dst_params[i]
+            _copy_into(_apply_sel(target, dst_sel), _apply_sel(src, src_sel))
+        return result
+
+    def update_block(self, dst_arr, *src_arrs, src_params, dst_params):
+        assert len(src_params) == len(dst_params)
+        dst = _materialize(upload(dst_arr))  # inputs are immutable (numpy_compute.py:136-138)
+        if dst_params[0][1]:
+            dst = _transpose_view(dst)
+        for i in range(len(src_params)):
+            src = upload(src_arrs[i])
+            src_sel, src_shape_bc, src_t = src_params[i]
+            if src_t:
+                src = _transpose_view(src)
+            if src_shape_bc is not None:
+                src = _reshape(src, src_shape_bc)
+            dst_sel, _t = dst_params[i]
+            _copy_into(_apply_sel(dst, dst_sel), _apply_sel(src, src_sel))
+        return dst
+
+    def update_block_by_index(self, dst_arr, src_arr, index_pairs):
+        result = _materialize(upload(dst_arr))
+        src = upload(src_arr)
+        for dst_index, src_index in index_pairs:
+            _copy_into(result[tuple(int(i) for i in dst_index)], src[tuple(int(i) for i in src_index)])
+        return result
+
+    def update_block_along_axis(self, dst_arr, src_arr, index_pairs, axis):
+        result = _materialize(upload(dst_arr))
+        src = upload(src_arr)
+        for dst_index, src_index in index_pairs:
+            _copy_into(result.select(axis, int(dst_index)), src.select(axis, int(src_index)))
+        return result
+
+    def transpose(self, arr):
+        return _transpose_view(upload(arr))
+
+    def reshape(self, arr, shape):
+        return _reshape(upload(arr), shape if isinstance(shape, (tuple, list)) else (shape,))
+
+    def split(self, arr, indices_or_sections, axis, transposed):
+        arr = upload(arr)
+        if transposed:
+            arr = _transpose_view(arr)
+        n = arr.shape[axis]
+        if isinstance(indices_or_sections, (int, np.integer)):
+            if n % indices_or_sections:
+                raise ValueError("array split does not result in an equal division")
+            step = n // int(indices_or_sections)
+            bounds = [(i * step, (i + 1) * step) for i in range(int(indices_or_sections))]
+        else:
+            cuts = [0] + [int(i) for i in indices_or_sections] + [n]
+            bounds = [(min(cuts[i], n), min(max(cuts[i + 1], cuts[i]), n)) for i in range(len(cuts) - 1)]
+        return [arr.narrow(axis, lo, max(hi - lo, 0)) for lo, hi in bounds]
+
+    def astype(self, arr, dtype_str):
+        arr = upload(arr)
+        return _materialize(arr, _lib.torch_dtype(_np_dtype(dtype_str)))
+
+    # ------------------------------------------------------------------ elementwise
+    def map_uop(self, op_name, arr, args, kwargs):
+        if args or kwargs:
+            raise NotImplementedError("map_uop(%s) with extra arguments" % op_name)
+        arr = upload(arr)
+        if op_name not in _lib.UOP_CODE:
+            raise NotImplementedError("unary ufunc %s" % op_name)
+        loop, out_dt = uop_types(op_name, _lib.numpy_dtype(arr.dtype))
+        out = _empty(arr.shape, out_dt)
+        if out.numel():
+            LIB.check(LIB.dll.nums_uop(_lib.UOP_CODE[op_name], _lib.dtype_code(loop), describe(arr),
+                                       describe(out), _stream()))
+        return out
+
+    def xlogy(self, arr_x, arr_y):
+        return self._elementwise("xlogy", upload(arr_x), upload(arr_y))
+
+    def _elementwise(self, name, a1, a2):
+        if name not in _lib.BOP_CODE:
+            raise NotImplementedError("binary ufunc %s" % name)
+        loop, out_dt = bop_types(name, _lib.numpy_dtype(a1.dtype), _lib.numpy_dtype(a2.dtype))
+        shape = torch.broadcast_shapes(tuple(a1.shape), tuple(a2.shape))
+        out = _empty(shape, out_dt)
+        if out.numel():
+            LIB.check(LIB.dll.nums_bop(_lib.BOP_CODE[name], _lib.dtype_code(loop), describe(a1), describe(a2),
+                                       describe(out), _stream()))
+        return out
+
+    def bop(self, op, a1, a2, a1_shape, a2_shape, a1_T, a2_T, axes):
+        a1 = _operand(a1, a1_shape, a1_T)
+        a2 = _operand(a2, a2_shape, a2_T)
+        if op == "tensordot":
+            return tensordot(a1, a2, axes)
+        return self._elementwise(_SHORT_OP_NAMES.get(op, op), a1, a2)
+
+    # ------------------------------------------------------------------ reductions
+    def reduce_axis(self, op_name, arr, axis, keepdims, transposed):
+        arr = upload(arr)
+        if op_name not in _lib.REDUCE_CODE:
+            raise NotImplementedError("reduce_axis(%s)" % op_name)
+        nd = arr.dim()
+        if axis is not None:
+            axis = int(axis)
+            if axis < 0:
+                axis += nd
+        # (arr.T).op(axis=a) == (arr.op(axis=nd-1-a)).T: reduce the stored array, transpose the view
+        flip = bool(transposed) and nd > 1
+        if flip and axis is not None:
+            axis = nd - 1 - axis
+        if not arr.is_contiguous():
+            arr = _materialize(arr)
+        in_dt = _lib.numpy_dtype(arr.dtype)
+        out_dt = getattr(np, op_name)(np.zeros((1,), dtype=in_dt)).dtype
+        shape = tuple(arr.shape)
+        if axis is None:
+            outer, red, inner = 1, int(np.prod(shape, dtype=np.int64)), 1
+            out_shape = (1,) * nd if keepdims else ()
+        else:
+            outer = int(np.prod(shape[:axis], dtype=np.int64))
+            red = shape[axis]
+            inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+            out_shape = shape[:axis] + ((1,) if keepdims else ()) + shape[axis + 1:]
+        out = _empty(out_shape, out_dt)
+        if out.numel():
+            if red == 0:
+                if op_name not in ("sum", "prod", "product", "any", "all"):
+                    raise ValueError("zero-size array to reduction operation %s which has no identity" % op_name)
+                LIB.check(LIB.dll.nums_fill(describe(out), 1.0 if op_name in ("prod", "product", "all") else 0.0,
+                                            _stream()))
+            else:
+                LIB.call_ws(LIB.dll.nums_reduce, arr.device,
+                            ((_lib.REDUCE_CODE[op_name], arr.data_ptr(), _lib.dtype_code(arr.dtype), outer, red,
+                              inner, out.data_ptr(), _lib.dtype_code(out.dtype)), (_stream(),)))
+        return _transpose_view(out) if flip else out
+
+    def sum_reduce(self, *arrs):
+        arrs = [upload(a) for a in arrs]
+        first = arrs[0]
+        dt = np.result_type(*[_lib.numpy_dtype(a.dtype) for a in arrs])
+        tdt = _lib.torch_dtype(dt)
+        prepared = []
+        for a in arrs:
+            if tuple(a.shape) != tuple(first.shape):
+                raise ValueError("sum_reduce needs same-shape blocks")
+            if a.dtype != tdt or not a.is_contiguous():
+                a = _materialize(a, tdt)
+            prepared.append(a)
+        out = _empty(first.shape, dt)
+        if out.numel():
+            ptrs = (_lib.ctypes.c_void_p * len(prepared))(*[a.data_ptr() for a in prepared])
+            LIB.check(LIB.dll.nums_sum_reduce(len(prepared), ptrs, _lib.dtype_code(tdt), out.numel(),
+                                              out.data_ptr(), _stream()))
+        return out
+
+    def arg_op(self, op_name, arr, block_slice, other_argoptima=None, other_optima=None):
+        if op_name not in ("argmin", "argmax"):
+            raise Exception("Unsupported arg op.")
+        arr = upload(arr)
+        if arr.dim() != 1:
+            arr = _reshape(arr, (arr.numel(),))
+        if not arr.is_contiguous():
+            arr = _materialize(arr)
+        out_index = _empty((), np.int64)
+        out_value = _empty((), _lib.numpy_dtype(arr.dtype))
+        ci = cv = None
+        if other_optima is not None:
+            ci = upload(other_argoptima, np.int64)
+            if ci.dtype != torch.int64:
+                ci = _materialize(ci, torch.int64)
+            cv = upload(other_optima)
+            if cv.dtype != arr.dtype:
+                cv = _materialize(cv, arr.dtype)
+        LIB.call_ws(LIB.dll.nums_arg_op, arr.device,
+                    ((1 if op_name == "argmax" else 0, arr.data_ptr(), _lib.dtype_code(arr.dtype), arr.numel(),
+                      int(block_slice.start or 0), ci.data_ptr() if ci is not None else None,
+                      cv.data_ptr() if cv is not None else None, out_index.data_ptr(), out_value.data_ptr()),
+                     (_stream(),)))
+        return out_index, out_value
+
+    def where(self, arr, x, y, block_slice_tuples):
+        if x is not None or y is not None:
+            raise NotImplementedError("three-argument where is not reachable from nums.numpy.where "
+                                      "(nums/numpy/api.py:379-381) and is not implemented")
+        arr = upload(arr)
+        if not arr.is_contiguous():
+            arr = _materialize(arr)
+        shape = tuple(arr.shape) if arr.dim() else (1,)
+        count = _empty((), np.int64)
+        LIB.call_ws(LIB.dll.nums_nonzero_count, arr.device,
+                    ((arr.data_ptr(), _lib.dtype_code(arr.dtype), arr.numel(), count.data_ptr()), (_stream(),)))
+        n = int(count.cpu().item())  # one 8-byte read-back: the caller fetches the shape anyway (application.py:588)
+        outs = [_empty((n,), np.int64) for _ in shape]
+        if n:
+            c = _lib.ctypes
+            shape_arr = (c.c_int64 * len(shape))(*shape)
+            offs = (c.c_int64 * len(shape))(*[int(s[0]) for s in block_slice_tuples][:len(shape)])
+            ptrs = (c.c_void_p * len(shape))(*[o.data_ptr() for o in outs])
+            LIB.call_ws(LIB.dll.nums_nonzero_fill, arr.device,
+                        ((arr.data_ptr(), _lib.dtype_code(arr.dtype), len(shape), shape_arr, offs, ptrs),
+                         (_stream(),)))
+        return tuple(outs + [(n,)])
+
+    def allclose(self, a, b, rtol, atol):
+        a, b = upload(a), upload(b)
+        dt = np.result_type(_lib.numpy_dtype(a.dtype), _lib.numpy_dtype(b.dtype))
+        tdt = _lib.torch_dtype(dt)
+        shape = torch.broadcast_shapes(tuple(a.shape), tuple(b.shape))
+        a = _materialize(a.expand(shape), tdt) if (a.dtype != tdt or tuple(a.shape) != tuple(shape) or not a.is_contiguous()) else a
+        b = _materialize(b.expand(shape), tdt) if (b.dtype != tdt or tuple(b.shape) != tuple(shape) or not b.is_contiguous()) else b
+        flag = _empty((), np.bool_)
+        LIB.call_ws(LIB.dll.nums_allclose, a.device,
+                    ((a.data_ptr(), b.data_ptr(), _lib.dtype_code(tdt), a.numel(), float(rtol), float(atol),
+                      flag.data_ptr()), (_stream(),)))
+        return flag
+
+    def logical_and(self, *bool_list):
+        flags = _empty((len(bool_list),), np.bool_)
+        for i, b in enumerate(bool_list):
+            _copy_into(flags[i], upload(b, np.bool_) if not isinstance(b, torch.Tensor) else b)
+        out = _empty((), np.bool_)
+        LIB.call_ws(LIB.dll.nums_reduce, flags.device,
+                    ((_lib.REDUCE_CODE["all"], flags.data_ptr(), _lib.BOOL, 1, len(bool_list), 1, out.data_ptr(),
+                      _lib.BOOL), (_stream(),)))
+        return out
+
+    # ------------------------------------------------------------------ dense linear algebra
+    def qr(self, *arrays, mode="reduced", axis=None):
+        if len(arrays) > 1:
+            assert axis is not None
+            arr = concatenate([upload(a) for a in arrays], axis)
+        else:
+            arr = upload(arrays[0])
+        if mode == "r":
+            return qr_r(arr)
+        if mode == "reduced":
+            return qr_reduced(arr)
+        raise NotImplementedError("qr mode %r" % (mode,))
+
+    def cholesky(self, arr):
+        return _single_cta_factor(LIB.dll.nums_cholesky, upload(arr), "Matrix is not positive definite")
+
+    def inv(self, arr):
+        return _single_cta_factor(LIB.dll.nums_inv, upload(arr), "Singular matrix")
+
+    def svd(self, arr):
+        arr = upload(arr)
+        raise NotImplementedError("svd is not implemented by libnumscuda yet")
+
+
+# ---------------------------------------------------------------------------------------------
+# contraction / factorisation helpers (module level so workloads can reuse them)
+# ---------------------------------------------------------------------------------------------
+def _as_matrix(t, rows, cols):
+    """View a tensor as a (rows, cols) matrix stored row-major or column-major without copying
+    when possible.  Returns (tensor, transposed_flag, pitch)."""
+    if t.is_contiguous():
+        return t, False, max(cols, 1)
+    tt = _transpose_view(t)
+    if tt.is_contiguous():  # fully reversed axes of a dense array: a (cols, rows) row-major matrix
+        return tt, True, max(rows, 1)
+    m = _materialize(t)
+    return m, False, max(cols, 1)
+
+
+def gemm_into(out, a, ta, lda, b, tb, ldb, m, n, k, accumulate=False):
+    LIB.call_ws(LIB.dll.nums_gemm, out.device,
+                ((_lib.dtype_code(out.dtype), int(ta), int(tb), m, n, k, a.data_ptr(), lda, b.data_ptr(), ldb,
+                  out.data_ptr(), max(n, 1), int(accumulate)), (_stream(),)))
+
+
+def tensordot(a1, a2, axes):
+    """np.tensordot(a1, a2, axes=k) for integer k (numpy_compute.py:231-232, blockarray.py:410-414)."""
+    if not isinstance(axes, (int, np.integer)):
+        raise NotImplementedError("tensordot with explicit axis lists")
+    axes = int(axes)
+    dt = np.result_type(_lib.numpy_dtype(a1.dtype), _lib.numpy_dtype(a2.dtype))
+    if dt == np.bool_:
+        raise NotImplementedError("tensordot on bool blocks")
+    tdt = _lib.torch_dtype(dt)
+    if a1.dtype != tdt:
+        a1 = _materialize(a1, tdt)
+    if a2.dtype != tdt:
+        a2 = _materialize(a2, tdt)
+    free1 = tuple(a1.shape[:a1.dim() - axes])
+    con1 = tuple(a1.shape[a1.dim() - axes:])
+    con2 = tuple(a2.shape[:axes])
+    free2 = tuple(a2.shape[axes:])
+    if con1 != con2:
+        raise ValueError("shape-mismatch for sum")
+    m = int(np.prod(free1, dtype=np.int64))
+    k = int(np.prod(con1, dtype=np.int64))
+    n = int(np.prod(free2, dtype=np.int64))
+    out = _empty(free1 + free2, dt)
+    if out.numel() == 0:
+        return out
+    # N-D operands: a fully reversed (lazy .T) view of a dense array is a transposed matrix only
+    # in the 2-D case; otherwise materialise.
+    if a1.dim() > 2 and not a1.is_contiguous():
+        a1 = _materialize(a1)
+    if a2.dim() > 2 and not a2.is_contiguous():
+        a2 = _materialize(a2)
+    A, ta, lda = _as_matrix(a1, m, k)
+    B, tb, ldb = _as_matrix(a2, k, n)
+    gemm_into(out, A, ta, lda, B, tb, ldb, m, n, k)
+    return out
+
+
+def concatenate(arrs, axis):
+    axis = int(axis)
+    shape = list(arrs[0].shape)
+    shape[axis] = sum(a.shape[axis] for a in arrs)
+    out = _empty(shape, _lib.numpy_dtype(arrs[0].dtype))
+    pos = 0
+    for a in arrs:
+        _copy_into(out.narrow(axis, pos, a.shape[axis]), a)
+        pos += a.shape[axis]
+    return out
+
+
+def qr_r(arr):
+    """R factor (k x n, k = min(m, n)) of a 2-D block: streaming Householder TSQR kernel."""
+    if arr.dim() != 2:
+        raise ValueError("qr needs a 2-D block")
+    if arr.dtype not in (torch.float64, torch.float32):
+        arr = _materialize(arr, torch.float64)
+    if not arr.is_contiguous():
+        arr = _materialize(arr)
+    m, n = arr.shape
+    r = _empty((min(m, n), n), _lib.numpy_dtype(arr.dtype))
+    LIB.call_ws(LIB.dll.nums_qr, arr.device,
+                ((_lib.dtype_code(arr.dtype), m, n, arr.data_ptr(), n, None, 0, r.data_ptr(), n), (_stream(),)))
+    return r
+
+
+def _inv_nocheck(a):
+    n = a.shape[0]
+    out = _empty((n, n), _lib.numpy_dtype(a.dtype))
+    LIB.call_ws(LIB.dll.nums_inv, a.device,
+                ((_lib.dtype_code(a.dtype), n, a.data_ptr(), n, out.data_ptr(), n, None), (_stream(),)))
+    return out
+
+
+def qr_reduced(arr):
+    """(Q, R) with Q (m x k) orthonormal.  R comes from the Householder TSQR kernel; Q is formed as
+    A R^-1 (what the reference itself does one level up, application.py:833-845) followed by one
+    re-orthogonalisation pass (R2 = qr_r(Q); Q <- Q R2^-1; R <- R2 R), which restores
+    orthogonality to working precision for any block whose condition number is below ~1/sqrt(eps).
+    """
+    if arr.dtype not in (torch.float64, torch.float32):
+        arr = _materialize(arr, torch.float64)
+    if not arr.is_contiguous():
+        arr = _materialize(arr)
+    m, n = arr.shape
+    k = min(m, n)
+    r = qr_r(arr)
+    lead = arr if k == n else _materialize(arr[:, :k])
+    r_sq = r if k == n else _materialize(r[:, :k])
+    dt = _lib.numpy_dtype(arr.dtype)
+    q = _empty((m, k), dt)
+    gemm_into(q, lead, False, k, _inv_nocheck(r_sq), False, k, m, k, k)
+    r2 = qr_r(q)
+    q2 = _empty((m, k), dt)
+    gemm_into(q2, q, False, k, _inv_nocheck(r2), False, k, m, k, k)
+    r_out = _empty((k, n), dt)
+    gemm_into(r_out, r2, False, k, r, False, n, k, n, k)
+    return q2, r_out
+
+
+def _single_cta_factor(fn, arr, message):
+    if arr.dim() != 2 or arr.shape[0] != arr.shape[1]:
+        raise np.linalg.LinAlgError("Last 2 dimensions of the array must be square")
+    if arr.dtype not in (torch.float64, torch.float32):
+        arr = _materialize(arr, torch.float64)
+    if not arr.is_contiguous():
+        arr = _materialize(arr)
+    n = arr.shape[0]
+    out = _empty((n, n), _lib.numpy_dtype(arr.dtype))
+    info = _empty((), np.int32) if CHECK_FACTORIZATION_STATUS else None
+    LIB.call_ws(fn, arr.device,
+                ((_lib.dtype_code(arr.dtype), n, arr.data_ptr(), n, out.data_ptr(), n,
+                  info.data_ptr() if info is not None else None), (_stream(),)))
+    if info is not None and int(info.cpu().item()) != 0:
+        raise np.linalg.LinAlgError(message)
+    return out
+
+
+def lr_grad_hess(X, y, beta):
+    """Fused g = X^T (mu - y), H = X^T diag(mu (1 - mu)) X for one row block (nums_lr_grad_hess).
+
+    Returns a 1-D tensor of d + d*d doubles (g followed by row-major H)."""
+    n, d = X.shape
+    out = _empty((d + d * d,), np.float64)
+    LIB.call_ws(LIB.dll.nums_lr_grad_hess, X.device,
+                ((n, d, X.data_ptr(), X.stride(0), y.data_ptr(), beta.data_ptr(), out.data_ptr()), (_stream(),)))
+    return out

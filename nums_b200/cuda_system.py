@@ -1,0 +1,128 @@
+"""``CudaSystem`` -- the system object that owns block placement for ``cuda_compute``.
+
+Mirror of the reference's ``System`` / ``SerialSystem`` (/root/reference/nums/core/systems/
+systems.py:31-142): it loads ``compute_module.ComputeCls``, exposes every kernel both through
+``system.call(name, ...)`` and as an attribute (``system.bop(...)``), strips ``syskwargs`` and
+runs the kernel in-process.  Unlike ``SerialSystem`` (identity put/get, systems.py:94-98) ``put``
+uploads a host array to HBM and ``get`` synchronises and downloads, as the fork's
+``CupySerialSystem`` does (gpu_systems.py:88-100).
+
+One process drives one GPU (``torch.distributed`` rank == device).  ``owner(grid_entry,
+grid_shape)`` implements the reference's placement rules so that SPMD drivers
+(``nums_b200.blocks``) know which rank computes a block:
+
+* ``"cyclic"``  -- ``grid_entry[axis] mod device_grid[axis]`` (BlockCyclicScheduler.get_cluster_entry,
+  schedulers.py:170-191);
+* ``"flat"``    -- row-major flattened entry ``mod world`` (the fork's CupyParallelSystem,
+  gpu_systems.py:163-164), which spreads tall-skinny grids over all devices.
+"""
+import inspect
+
+import numpy as np
+import torch
+
+from nums_b200 import cuda_compute
+
+
+class CudaSystem(object):
+
+    def __init__(self, compute_module=cuda_compute, device=None, rank=0, world_size=1,
+                 device_grid=None, placement="flat"):
+        self.compute_module = compute_module
+        self.compute_imp = compute_module.ComputeCls
+        if getattr(compute_module, "RNG", None) is None:
+            raise Exception("No random number generator implemented for compute module %s" % compute_module)
+        self.rng_cls = compute_module.RNG
+        self.methods = {}
+        self.remote_functions = {}
+        self.rank = int(rank)
+        self.world_size = int(world_size)
+        self.device_grid = tuple(device_grid) if device_grid is not None else (self.world_size, 1)
+        self.placement = placement
+        self._device = device
+        self._imp = None
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def init(self):
+        if self._device is None and torch.cuda.is_available():
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        if self._device is not None and self._device.type == "cuda":
+            torch.cuda.set_device(self._device)
+        self._imp = self.compute_imp()
+        for name, fn in inspect.getmembers(self._imp, predicate=inspect.ismethod):
+            if name.startswith("_"):
+                continue
+            self.remote_functions[name] = fn
+            self.methods[name] = self._make_callable(name)
+
+    def shutdown(self):
+        self.methods.clear()
+        self.remote_functions.clear()
+
+    def _make_callable(self, name):
+        def kernel(*args, **kwargs):
+            return self.call(name, *args, **kwargs)
+        kernel.__name__ = name
+        return kernel
+
+    def __getattr__(self, name):
+        # only reached when normal lookup fails: kernel names are routed to ``call``
+        methods = self.__dict__.get("methods", {})
+        if name in methods:
+            return methods[name]
+        raise AttributeError(name)
+
+    # -- object store ----------------------------------------------------------------------------
+    def put(self, value):
+        return cuda_compute.upload(value)
+
+    def get(self, object_ids):
+        if isinstance(object_ids, (list, tuple)):
+            return type(object_ids)(self.get(o) for o in object_ids) if isinstance(object_ids, tuple) \
+                else [self.get(o) for o in object_ids]
+        return cuda_compute.download(object_ids)
+
+    def remote(self, function, remote_params):
+        return function
+
+    def register(self, name, func, remote_params=None):
+        if name in self.remote_functions:
+            return
+        self.remote_functions[name] = func
+        self.methods[name] = self._make_callable(name)
+
+    def nodes(self):
+        return [{"Resources": {"node:%d" % r: 1.0}} for r in range(self.world_size)]
+
+    def get_rng(self, seed):
+        return self.rng_cls(seed)
+
+    # -- dispatch -----------------------------------------------------------------------------------
+    def call(self, name, *args, **kwargs):
+        kwargs = dict(kwargs)
+        kwargs.pop("syskwargs", None)
+        return self.remote_functions[name](*args, **kwargs)
+
+    def call_with_options(self, name, args, kwargs, options):
+        return self.call(name, *args, **kwargs)
+
+    def get_options(self, cluster_entry, cluster_shape):
+        return {"resources": {"node:%d" % self.rank: 1.0 / 10 ** 4}}
+
+    def get_block_addresses(self, grid):
+        return {entry: "node:%d" % self.owner(entry, grid.grid_shape) for entry in grid.get_entry_iterator()}
+
+    # -- placement ------------------------------------------------------------------------------------
+    def owner(self, grid_entry, grid_shape):
+        """Rank that owns / computes the block at ``grid_entry`` of a grid of ``grid_shape``."""
+        if self.world_size == 1 or len(grid_entry) == 0:
+            return 0
+        if self.placement == "flat":
+            flat = int(np.ravel_multi_index(tuple(grid_entry), tuple(grid_shape)))
+            return flat % self.world_size
+        dg = self.device_grid
+        coords = [grid_entry[i] % dg[i] if i < len(grid_entry) else 0 for i in range(len(dg))]
+        return int(np.ravel_multi_index(tuple(coords), dg))
+
+    def synchronize(self):
+        torch.cuda.current_stream().synchronize()
