@@ -180,7 +180,7 @@ class _Lib(object):
             self._ws[key] = ws
         return ws
 
-    def call_ws(self, fn, device, *args_before_ws_and_after):
+    def call_ws(self, fn, device, args_before_ws_and_after):
         """Call ``fn(*before, ws, ws_bytes, *after)``; retry once with a larger workspace."""
         before, after = args_before_ws_and_after
         ws = self.workspace(device)

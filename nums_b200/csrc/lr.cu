@@ -184,8 +184,9 @@ lr_grad_hess_kernel(const double* __restrict__ X, int64_t ldx, const double* __r
     if (i < d) src = i;
     else {
       const int r = (i - d) / d, c = (i - d) - r * d;
-      // blocks below the block diagonal were not computed: read the mirrored entry
-      src = (r / 8 <= c / 8) ? D8 + r * D8 + c : D8 + c * D8 + r;
+      // only the upper triangle is read (blocks below the block diagonal were never computed, and
+      // mirroring inside diagonal blocks makes H exactly symmetric)
+      src = (r <= c) ? D8 + r * D8 + c : D8 + c * D8 + r;
     }
     double acc = 0.0;
 #pragma unroll
@@ -237,9 +238,9 @@ extern "C" int nums_lr_grad_hess(int64_t n, int64_t d, const double* X, int64_t 
   using namespace nums;
   NUMS_REQUIRE(n >= 1 && d >= 1, "lr_grad_hess: empty block");
   NUMS_REQUIRE(X && y && beta && out, "lr_grad_hess: null pointer");
-  if (d > 64 || d % 2 != 0 || ldx % 2 != 0 || (reinterpret_cast<uintptr_t>(X) & 15u) != 0)
+  if (d > 48 || d % 2 != 0 || ldx % 2 != 0 || (reinterpret_cast<uintptr_t>(X) & 15u) != 0)
     NUMS_FAIL(NUMS_ERR_UNSUPPORTED,
-              "lr_grad_hess: needs even d <= 64, even row pitch and a 16-byte aligned X (d=%lld, ldx=%lld)",
+              "lr_grad_hess: needs even d <= 48, even row pitch and a 16-byte aligned X (d=%lld, ldx=%lld)",
               (long long)d, (long long)ldx);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch ((d + 7) / 8) {
@@ -249,8 +250,6 @@ extern "C" int nums_lr_grad_hess(int64_t n, int64_t d, const double* X, int64_t 
     case 4: return launch_lr<4>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
     case 5: return launch_lr<5>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
     case 6: return launch_lr<6>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
-    case 7: return launch_lr<7>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
-    case 8: return launch_lr<8>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
   }
   NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "lr_grad_hess: d = %lld", (long long)d);
 }

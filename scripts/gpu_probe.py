@@ -52,7 +52,7 @@ def main():
     system.init()
     which = set(sys.argv[1:]) or {"copy", "bop", "gemm", "reduce", "lr", "qr", "gemv"}
     props = torch.cuda.get_device_properties(0)
-    record("device", name=props.name, sms=props.multi_processor_count, mem_gb=props.total_memory / 2 ** 30)
+    record("device", gpu=props.name, sms=props.multi_processor_count, mem_gb=props.total_memory / 2 ** 30)
 
     if "copy" in which:
         a = torch.empty(1 << 28, dtype=torch.float64, device=dev)  # 2 GiB
