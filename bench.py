@@ -1,0 +1,502 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline workloads on B200 through ``cuda_compute``.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Headline line (one JSON object on stdout, printed by rank 0): BASELINE.json configs[1] --
+blocked float64 matmul 16384 x 16384 @ 16384 x 16384 on an 8 x 8 grid of 2048 x 2048 blocks,
+``metric`` = FP64 TFLOP/s of the whole job.  A "step" is one full ``C = A @ B`` over the block
+grid through the per-block kernel interface (512 ``bop('tensordot')`` + 448 ``bop('add')``
+calls at N = 1; SUMMA at N > 1).  The other parts of BASELINE.json's metric (bop
+GB/s, TSQR TFLOP/s, Newton-LR s/iter) are measured in the same run and reported under
+``"workloads"``.
+
+``--impl reference`` times the reference's CPU implementation of the same path (the NumPy /
+OpenBLAS kernels it calls, driven by the same block-level call sequence) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_MATMUL = 16384
+BLOCK = 2048
+GRID = N_MATMUL // BLOCK
+FLOPS_PER_STEP = 2.0 * N_MATMUL ** 3
+FLOPS_PER_BLOCK_GEMM = 2.0 * BLOCK ** 3
+NOMINAL_FP64_TFLOPS = 40.0     # B200 datasheet FP64 / FP64-tensor figure (not measured)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.thread, self.index = [], None, None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# data
+# ------------------------------------------------------------------------------------------------
+def matmul_blocks_host(seed_a=3, seed_b=4, pinned=True):
+    """The 8 x 8 grids of 2048 x 2048 float64 blocks of A and B (standard normal, seeded per block
+    so that no 2 GiB host array has to be generated serially)."""
+    import torch
+    out = {}
+    for name, seed in (("A", seed_a), ("B", seed_b)):
+        blocks = {}
+        for i in range(GRID):
+            for j in range(GRID):
+                rng = np.random.default_rng([seed, i, j])
+                arr = rng.standard_normal((BLOCK, BLOCK))
+                if pinned:
+                    t = torch.empty((BLOCK, BLOCK), dtype=torch.float64, pin_memory=True)
+                    t.numpy()[...] = arr
+                    arr = t.numpy()
+                blocks[(i, j)] = arr
+        out[name] = blocks
+    return out["A"], out["B"]
+
+
+def blockarray_from_blocks(system, host_blocks):
+    from nums_b200.blocks import BlockArray
+    from nums_b200.grid import ArrayGrid
+    ba = BlockArray(ArrayGrid((N_MATMUL, N_MATMUL), (BLOCK, BLOCK), "float64"), system)
+    for entry, arr in host_blocks.items():
+        ba.blocks[entry].oid = system.put(arr)
+    return ba
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's NumPy kernels driven by the same block-level call sequence
+# ------------------------------------------------------------------------------------------------
+def cpu_matmul_sample(c_blocks, a_host, b_host):
+    """Computes `c_blocks` C blocks of the 8 x 8 blocked matmul exactly as BlockArray._tensordot
+    does (8 tensordot + 7 add kernel calls per C block, blockarray.py:460-472).  Returns seconds."""
+    from oracle.cpu_system import OracleSystem
+    system = OracleSystem()
+    shape = (BLOCK, BLOCK)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(GRID):
+        for j in range(GRID):
+            if done >= c_blocks:
+                break
+            acc = None
+            for k in range(GRID):
+                sk = {"grid_entry": (i, j), "grid_shape": (GRID, GRID)}
+                dot = system.bop("tensordot", a_host[(i, k)], b_host[(k, j)], shape, shape, False, False, axes=1, syskwargs=sk)
+                acc = dot if acc is None else system.bop("add", acc, dot, shape, shape, False, False, axes=None, syskwargs=sk)
+            done += 1
+    return time.perf_counter() - t0, done
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        blas = [p for p in threadpool_info() if p.get("user_api") == "blas"]
+        if blas:
+            return int(blas[0]["num_threads"]), blas[0].get("internal_api", "blas")
+    except Exception:  # noqa: BLE001
+        pass
+    return len(os.sched_getaffinity(0)), "unknown"
+
+
+def measure_cpu(a_host, b_host, target_seconds=12.0):
+    """Bounded sample of the CPU path: as many C blocks as fit in about `target_seconds`."""
+    probe, _ = cpu_matmul_sample(1, a_host, b_host)
+    blocks = int(max(1, min(GRID * GRID, target_seconds // max(probe, 1e-3))))
+    seconds, done = cpu_matmul_sample(blocks, a_host, b_host) if blocks > 1 else (probe, 1)
+    flops = done * GRID * FLOPS_PER_BLOCK_GEMM
+    threads, api = cpu_threads()
+    return {"value": flops / seconds / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": "port",
+            "sample": "%d of %d C blocks (8 tensordot + 7 add calls each) of the 16384^2 blocked matmul, "
+                      "NumPy %s / %s with %d threads, %.1f s" % (done, GRID * GRID, np.__version__, api, threads, seconds)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    a_host, b_host = matmul_blocks_host(pinned=False)
+    probe, _ = cpu_matmul_sample(1, a_host, b_host)
+    per_step_blocks = int(max(1, min(GRID * GRID, 20.0 // max(probe, 1e-3) // max(args.steps + args.warmup, 1))))
+    for _ in range(args.warmup):
+        cpu_matmul_sample(per_step_blocks, a_host, b_host)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        _, d = cpu_matmul_sample(per_step_blocks, a_host, b_host)
+        done += d
+    seconds = time.perf_counter() - t0
+    threads, api = cpu_threads()
+    value = done * GRID * FLOPS_PER_BLOCK_GEMM / seconds / 1e12
+    sample = ("each step = %d of %d C blocks of the 16384^2 blocked matmul (8 tensordot + 7 add kernel calls per "
+              "block), reference numpy_compute kernels (NumPy %s / %s)" % (per_step_blocks, GRID * GRID, np.__version__, api))
+    line = {
+        "impl": "reference", "metric": "blocked_matmul_fp64_tflops", "value": value, "unit": "TFLOP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "blocked matmul float64 16384x16384 @ 16384x16384, 8x8 grid of 2048x2048 blocks "
+                               "(BASELINE.json configs[1])", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def cuda_time(fn, sync):
+    import torch
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    start.record()
+    fn()
+    end.record()
+    end.synchronize()
+    sync()
+    return start.elapsed_time(end) * 1e-3
+
+
+def other_workloads(system, quick):
+    """bop (cfg1), TSQR (cfg3) and Newton LR (cfg4) on one GPU; device-timed, synthetic data."""
+    import torch
+    from nums_b200 import blocks as nb
+    from nums_b200 import cuda_compute as cc
+    from nums_b200.grid import ArrayGrid
+    out = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    app = nb.ArrayApp(system)
+
+    def timed(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(iters):
+            times.append(cuda_time(fn, torch.cuda.synchronize))
+        return float(np.median(times))
+
+    def device_blockarray(shape, block_shape, fill):
+        ba = nb.BlockArray(ArrayGrid(shape, block_shape, "float64"), system)
+        for entry in ba.grid.get_entry_iterator():
+            ba.blocks[entry].oid = fill(ba.grid.get_block_shape(entry))
+        return ba
+
+    # cfg1: u + v, u * v on two 1e8-element vectors in 8 blocks (24 B / element)
+    n = 100_000_000
+    U = device_blockarray((n,), (n // 8,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
+    V = device_blockarray((n,), (n // 8,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
+    for name, fn in (("add", lambda: (U + V).touch()), ("mul", lambda: (U * V).touch())):
+        t = timed(fn, 5 if quick else 20)
+        out["bop_" + name] = {"value": 24.0 * n / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
+                              "workload": "float64 %s of two 1e8-element BlockArrays, 8 blocks (inputs 1.6 GB > L2)" % name}
+    del U, V
+
+    # cfg4: Newton LR 11M x 28, 8 row blocks
+    N, d, G = 11_000_000, 28, 8
+    nb_rows = N // G
+    X = device_blockarray((N, d), (nb_rows, d), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
+    theta = torch.randn(d, dtype=torch.float64, device=dev) / np.sqrt(d)
+    y = nb.BlockArray(ArrayGrid((N,), (nb_rows,), "float64"), system)
+    for (i,) in y.grid.get_entry_iterator():
+        xb = X.blocks[i, 0].oid
+        p = torch.sigmoid(xb @ theta)
+        y.blocks[i].oid = (torch.rand(xb.shape[0], dtype=torch.float64, device=dev) < p).to(torch.float64)
+    model = nb.LogisticRegression(app)
+    iters_unfused = 2 if quick else 4
+
+    def unfused():
+        beta0 = app.zeros((d,), (d,), np.float64)
+        nb.newton(app, model, beta0, X, y, app.scalar(1e-300), iters_unfused)
+    t = timed(unfused, 1 if quick else 2)
+    out["newton_lr_interface_path"] = {
+        "value": t / iters_unfused, "unit": "s/iter",
+        "workload": "glms.newton call sequence (~15 kernel calls per block per iteration) on 11M x 28 float64, 8 row blocks",
+        "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_unfused) / 1e9}
+    from nums_b200 import multi_gpu
+    comm = multi_gpu.Comm()
+    xs = [X.blocks[i, 0].oid for i in range(G)]
+    ys = [y.blocks[i].oid for i in range(G)]
+    iters_fused = 10
+
+    def fused():
+        multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters_fused, cc.lr_grad_hess)
+    t = timed(fused, 2 if quick else 3)
+    out["newton_lr_fused"] = {
+        "value": t / iters_fused, "unit": "s/iter",
+        "workload": "Newton iteration with the fused gradient+Hessian kernel, 11M x 28 float64, 8 row blocks, 10 iterations",
+        "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_fused) / 1e9}
+    del X, y, xs, ys
+
+    # cfg3: TSQR 16M x 128 (17.2 GB), 8 row blocks: R only, and (Q, R)
+    m, ncol, G = 16_777_216, 128, 8
+    X = device_blockarray((m, ncol), (m // G, ncol), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
+    flops_r = 2.0 * m * ncol ** 2 - 2.0 * ncol ** 3 / 3.0
+    t = timed(lambda: app.indirect_tsr(X).touch(), 1 if quick else 3)
+    out["tsqr_r"] = {"value": flops_r / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
+                     "workload": "indirect_tsr on 16777216 x 128 float64, 8 row blocks (2mn^2 - 2n^3/3 flop)"}
+    t = timed(lambda: app.indirect_tsqr(X)[0].touch(), 1 if quick else 3)
+    out["tsqr_qr"] = {"value": (flops_r + 2.0 * m * ncol ** 2) / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
+                      "workload": "indirect_tsqr (Q = X R^-1, R) on 16777216 x 128 float64, 8 row blocks"}
+    del X
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from nums_b200 import _lib, multi_gpu
+    from nums_b200.cuda_system import CudaSystem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    comm = multi_gpu.Comm()
+    system = CudaSystem(rank=rank, world_size=world)
+    system.init()
+    LIB = _lib.LIB
+
+    def sync_all():
+        torch.cuda.synchronize()
+        comm.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs (host, pinned) -----------------------------------------------------------------------
+    a_host, b_host = matmul_blocks_host(pinned=True)
+
+    if world == 1:
+        from nums_b200.blocks import BlockArray  # noqa: F401
+        A = blockarray_from_blocks(system, a_host)
+        B = blockarray_from_blocks(system, b_host)
+
+        def step_resident():
+            (A @ B).touch()
+
+        def step_e2e():
+            a = blockarray_from_blocks(system, a_host)
+            b = blockarray_from_blocks(system, b_host)
+            c = a @ b
+            return c.get()
+        parallelism = "1 GPU, BlockArray._tensordot call sequence (512 tensordot + 448 add kernel calls)"
+    else:
+        pr, pc = multi_gpu.device_grid(world)
+        like = torch.empty((1,), dtype=torch.float64, device="cuda")
+        summa = multi_gpu.SummaMatmul(system, comm, GRID, BLOCK, like)
+        mine_a = {e: system.put(v) for e, v in a_host.items() if summa.owner_a(*e) == rank}
+        mine_b = {e: system.put(v) for e, v in b_host.items() if summa.owner_b(*e) == rank}
+
+        def step_resident():
+            summa.run(mine_a, mine_b)
+            torch.cuda.synchronize()
+
+        def step_e2e():
+            la = {e: system.put(v) for e, v in a_host.items() if summa.owner_a(*e) == rank}
+            lb = {e: system.put(v) for e, v in b_host.items() if summa.owner_b(*e) == rank}
+            c = summa.run(la, lb)
+            return {e: system.get(v) for e, v in c.items()}
+        parallelism = "SUMMA on a %dx%d device grid, NCCL broadcasts of A(:,k)/B(k,:) blocks" % (pr, pc)
+
+    # ---- timed: HBM-resident ---------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    sync_all()
+    launches0 = LIB.dll.nums_launch_count()
+    t_mark0 = sampler.mark()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        step_resident()
+    end.record()
+    end.synchronize()
+    sync_all()
+    t_mark1 = sampler.mark()
+    launches = LIB.dll.nums_launch_count() - launches0
+    elapsed = torch.tensor([start.elapsed_time(end) * 1e-3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    seconds = float(elapsed.item())
+    value = FLOPS_PER_STEP * args.steps / seconds / 1e12
+
+    # ---- timed: end to end (pinned host -> HBM -> kernels -> host) ------------------------------------------
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    sync_all()
+    e2e_seconds = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_seconds, op=dist.ReduceOp.MAX)
+    e2e_value = FLOPS_PER_STEP * e2e_steps / float(e2e_seconds.item()) / 1e12
+    bytes_matrix = 8 * N_MATMUL * N_MATMUL
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0, N == 1 extras: roofline of the dominant kernel, CPU baseline, other workloads ----------------
+    sampler.stop()
+    clocks = sampler.summary(t_mark0, t_mark1)
+    roofline = None
+    cpu_baseline = None
+    workloads = None
+    if world == 1:
+        a0, b0 = A.blocks[0, 0].oid, B.blocks[0, 0].oid
+        shape = (BLOCK, BLOCK)
+
+        def gemm_burst():
+            for _ in range(64):
+                system.bop("tensordot", a0, b0, shape, shape, False, False, axes=1, syskwargs={})
+        gemm_burst()
+        t_gemm = cuda_time(gemm_burst, torch.cuda.synchronize) / 64
+        big = torch.randn((8192, 8192), dtype=torch.float64, device="cuda")
+        torch.matmul(big, big)
+        t_cublas = min(cuda_time(lambda: torch.matmul(big, big), torch.cuda.synchronize) for _ in range(3))
+        del big
+        peak = 2.0 * 8192 ** 3 / t_cublas / 1e12
+        achieved = FLOPS_PER_BLOCK_GEMM / t_gemm / 1e12
+        roofline = {"bound": "tensor", "kernel": "dgemm_dmma_kernel (FP64 DMMA m8n8k4, 128x128x16 tiles)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": "cuBLAS DGEMM (torch.matmul float64 8192^3) measured live in this run; "
+                                   "MEASURED_PEAKS.json has no FP64 entry (only bf16 and HBM)",
+                    "frac_of_nominal_40TF": achieved / NOMINAL_FP64_TFLOPS,
+                    "algorithmic_flops_per_launch": FLOPS_PER_BLOCK_GEMM,
+                    "avg_launch_ms": t_gemm * 1e3, "traffic": None}
+        try:
+            with open(os.path.join(ROOT, "profiles", "dgemm_traffic.json")) as f:
+                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+        del A, B
+        torch.cuda.empty_cache()
+        if not args.skip_cpu:
+            cpu_baseline = measure_cpu(a_host, b_host)
+        if not args.skip_workloads:
+            workloads = other_workloads(system, quick=args.quick)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    if workloads and peaks.get("hbm_gbs"):
+        for key in ("bop_add", "bop_mul"):
+            workloads[key]["frac_of_measured_hbm"] = workloads[key]["value"] / peaks["hbm_gbs"]
+
+    line = {
+        "metric": "blocked_matmul_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "blocked matmul float64 16384x16384 @ 16384x16384, 8x8 grid of 2048x2048 blocks "
+                               "(BASELINE.json configs[1])",
+                   "parallelism": parallelism,
+                   "l2_policy": "inputs (2 x 2.1 GB) and output (2.1 GB) exceed the 126 MB L2; no flush needed"},
+        "e2e": {"value": e2e_value, "unit": "TFLOP/s",
+                "h2d_bytes_per_step": 2 * bytes_matrix, "d2h_bytes_per_step": bytes_matrix, "steps": e2e_steps,
+                "what": "pinned host blocks -> system.put -> A @ B through the block kernel interface -> C.get() on the host"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "workloads": workloads,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nums_b200", choices=["nums_b200", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-workloads", action="store_true", help="only the headline matmul")
+    ap.add_argument("--quick", action="store_true", help="fewer repetitions of the secondary workloads")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,6 +105,8 @@ const char* nums_last_error(void);
 size_t nums_last_workspace_request(void);
 /* Number of SMs of the current device (148 on B200); <0 on error. */
 int nums_sm_count(void);
+/* Total number of CUDA kernels this library has launched in the process so far. */
+uint64_t nums_launch_count(void);
 
 /* ---- elementwise ---------------------------------------------------------------------
  * out = ufunc(a, b) with NumPy broadcasting of a and b against out->shape (right aligned,

@@ -130,6 +130,7 @@ class _Lib(object):
             "nums_last_error": ([], c.c_char_p),
             "nums_last_workspace_request": ([], Z),
             "nums_sm_count": ([], c.c_int),
+            "nums_launch_count": ([], c.c_uint64),
             "nums_bop": ([I, I, A, A, A, P], I),
             "nums_uop": ([I, I, A, A, P], I),
             "nums_sum_reduce": ([I, c.POINTER(P), I, L, P, P], I),
@@ -153,7 +154,7 @@ class _Lib(object):
             fn.argtypes = argtypes
             fn.restype = restype
 
-    EXPORTS = ("nums_abi_version nums_last_error nums_last_workspace_request nums_sm_count nums_bop "
+    EXPORTS = ("nums_abi_version nums_last_error nums_last_workspace_request nums_sm_count nums_launch_count nums_bop "
                "nums_uop nums_sum_reduce nums_fill nums_arange nums_eye nums_reduce nums_arg_op "
                "nums_allclose nums_nonzero_count nums_nonzero_fill nums_gemm nums_qr nums_inv "
                "nums_cholesky nums_svd nums_lr_grad_hess").split()

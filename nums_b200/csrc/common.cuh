@@ -14,6 +14,7 @@ namespace nums {
 // ---- error plumbing --------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void set_workspace_request(size_t bytes);
+void count_launch();
 int sm_count();
 
 #define NUMS_FAIL(code, ...)      \
@@ -35,7 +36,13 @@ int sm_count();
                 __FILE__, __LINE__);                                              \
   } while (0)
 
-#define NUMS_LAUNCH_OK() NUMS_CUDA_OK(cudaGetLastError())
+// Every kernel launch of the library goes through this macro: it bumps the process-wide launch
+// counter (nums_launch_count) and surfaces launch-configuration errors.
+#define NUMS_LAUNCH_OK()                  \
+  do {                                    \
+    ::nums::count_launch();               \
+    NUMS_CUDA_OK(cudaGetLastError());     \
+  } while (0)
 
 #define NUMS_NEED_WS(need, have)                                                   \
   do {                                                                             \

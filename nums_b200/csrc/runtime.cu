@@ -1,7 +1,11 @@
 // Library plumbing: thread-local error text, workspace requests, array/layout validation.
+#include <atomic>
 #include "common.cuh"
 
 namespace nums {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local char g_error[512] = "";
 static thread_local size_t g_ws_request = 0;
@@ -121,4 +125,5 @@ int nums_abi_version(void) { return NUMS_ABI_VERSION; }
 const char* nums_last_error(void) { return nums::g_error; }
 size_t nums_last_workspace_request(void) { return nums::g_ws_request; }
 int nums_sm_count(void) { return nums::sm_count(); }
+uint64_t nums_launch_count(void) { return nums::g_launches.load(std::memory_order_relaxed); }
 }

@@ -13,35 +13,12 @@ def load_golden(name):
         return pickle.load(f)
 
 
-class OracleSystem(object):
-    """SerialSystem-shaped object over ``oracle.np_oracle.OracleCompute`` that records every call.
+from oracle.cpu_system import OracleSystem as _OracleSystem
 
-    Test infrastructure: lets the host-side drivers (nums_b200.blocks) run on CPU so that their
-    kernel-call sequences can be compared with the reference's recorded ones."""
 
-    def __init__(self):
-        from oracle.np_oracle import OracleCompute
-        self.imp = OracleCompute()
-        self.trace = []
-
-    def put(self, value):
-        return np.asarray(value)
-
-    def get(self, oids):
-        if isinstance(oids, list):
-            return [self.get(o) for o in oids]
-        return oids
-
-    def call(self, name, *args, **kwargs):
-        from oracle.make_golden import call_signature, freeze
-        self.trace.append(call_signature(name, freeze(args), freeze(kwargs)))
-        kwargs = {k: v for k, v in kwargs.items() if k != "syskwargs"}
-        return getattr(self.imp, name)(*args, **kwargs)
-
-    def __getattr__(self, name):
-        if name.startswith("_") or not hasattr(type(self.__dict__.get("imp")), name):
-            raise AttributeError(name)
-        return lambda *a, **k: self.call(name, *a, **k)
+def OracleSystem():
+    """Recording oracle-backed system (see oracle/cpu_system.py)."""
+    return _OracleSystem(record=True)
 
 
 def canon_r(R):
