@@ -174,6 +174,28 @@ int nums_gemm(int dtype, int trans_a, int trans_b, int64_t m, int64_t n, int64_t
               const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
               int accumulate, void* ws, size_t ws_bytes, void* stream);
 
+/* Grouped / chained contraction: for every problem p,
+ *     C_p[m,n] = (Cin_p ? Cin_p : 0) + sum over its terms t of op(A_t)[m,k_t] . op(B_t)[k_t,n]
+ * in ONE launch whose CTAs walk the tiles of all problems.  This is the k-chain of
+ * BlockArray._tensordot (blockarray.py:460-472: `dot`, then `result_block += dot` per k)
+ * accumulated in registers instead of through separate `add` kernels, for all result blocks at
+ * once.  float64 only; every operand must be 16-byte aligned with an even pitch.  The tables are
+ * HOST arrays (copied to the workspace by the call).  trans_a / trans_b apply to all terms. */
+typedef struct {
+  const void* A;
+  const void* B;
+  int64_t lda, ldb, k;
+} nums_gemm_term_t;
+typedef struct {
+  void* C;
+  const void* Cin;
+  int64_t ldc, ldcin, m, n;
+  int32_t term_begin, term_count;
+} nums_gemm_problem_t;
+int nums_gemm_grouped(int dtype, int trans_a, int trans_b, int nproblems,
+                      const nums_gemm_problem_t* problems_host, int nterms,
+                      const nums_gemm_term_t* terms_host, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- factorisations ----------------------------------------------------------------------
  * QR of a row-major m x n matrix (np.linalg.qr, numpy_compute.py:240-246).
  * R is k x n (k = min(m,n)), row-major, written with zeros below the diagonal.

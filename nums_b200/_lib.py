@@ -56,6 +56,17 @@ class NumsArray(ctypes.Structure):
                 ("shape", ctypes.c_int64 * MAX_DIMS), ("stride", ctypes.c_int64 * MAX_DIMS)]
 
 
+class GemmTerm(ctypes.Structure):       # nums_gemm_term_t
+    _fields_ = [("A", ctypes.c_void_p), ("B", ctypes.c_void_p), ("lda", ctypes.c_int64),
+                ("ldb", ctypes.c_int64), ("k", ctypes.c_int64)]
+
+
+class GemmProblem(ctypes.Structure):    # nums_gemm_problem_t
+    _fields_ = [("C", ctypes.c_void_p), ("Cin", ctypes.c_void_p), ("ldc", ctypes.c_int64),
+                ("ldcin", ctypes.c_int64), ("m", ctypes.c_int64), ("n", ctypes.c_int64),
+                ("term_begin", ctypes.c_int32), ("term_count", ctypes.c_int32)]
+
+
 def dtype_code(dt):
     """torch / numpy dtype -> nums_dtype_t; raises for dtypes the library has no loops for."""
     if isinstance(dt, torch.dtype):
@@ -143,6 +154,7 @@ class _Lib(object):
             "nums_nonzero_count": ([P, I, L, P, P, Z, P], I),
             "nums_nonzero_fill": ([P, I, I, c.POINTER(L), c.POINTER(L), c.POINTER(P), P, Z, P], I),
             "nums_gemm": ([I, I, I, L, L, L, P, L, P, L, P, L, I, P, Z, P], I),
+            "nums_gemm_grouped": ([I, I, I, I, c.POINTER(GemmProblem), I, c.POINTER(GemmTerm), P, Z, P], I),
             "nums_qr": ([I, L, L, P, L, P, L, P, L, P, Z, P], I),
             "nums_inv": ([I, L, P, L, P, L, P, P, Z, P], I),
             "nums_cholesky": ([I, L, P, L, P, L, P, P, Z, P], I),
@@ -156,7 +168,7 @@ class _Lib(object):
 
     EXPORTS = ("nums_abi_version nums_last_error nums_last_workspace_request nums_sm_count nums_launch_count nums_bop "
                "nums_uop nums_sum_reduce nums_fill nums_arange nums_eye nums_reduce nums_arg_op "
-               "nums_allclose nums_nonzero_count nums_nonzero_fill nums_gemm nums_qr nums_inv "
+               "nums_allclose nums_nonzero_count nums_nonzero_fill nums_gemm nums_gemm_grouped nums_qr nums_inv "
                "nums_cholesky nums_svd nums_lr_grad_hess").split()
 
     # -- error handling ---------------------------------------------------------------------

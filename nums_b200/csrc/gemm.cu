@@ -3,7 +3,7 @@
 //
 //   * f64 GEMM: FP64 tensor pipe.  On sm_100a every mma.sync f64 shape lowers to DMMA.8x8x4
 //     (checked with cuobjdump), so the kernel is written directly against m8n8k4 fragments:
-//     128x128x16 CTA tiles, 8 warps of 32x64, a 4-stage cp.async shared-memory ring padded so
+//     128x128x32 CTA tiles, 8 warps of 32x64, a 3-stage cp.async shared-memory ring padded so
 //     that every fragment read is bank-conflict free, optional split-K for small outputs with
 //     long contractions (X^T X, the LR Hessian).  Operands may be stored transposed
 //     (BlockArray.T is lazy, base.py:72-85), handled by the shared-memory layout, not by a
@@ -12,6 +12,7 @@
 //     HBM-bound streaming kernels.
 //   * everything else (f32, exact integer tensordot from tests/core/array/test_bop.py:38-42,
 //     unaligned f64): a plain shared-memory tiled kernel.
+#include <vector>
 #include "common.cuh"
 
 namespace nums {
@@ -22,8 +23,8 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ======================================================================================
 // FP64 DMMA GEMM
 // ======================================================================================
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int kStages = 4;
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int kStages = 3;
 constexpr int kGemmThreads = 256;
 constexpr int kPad = 4;  // row pitch == 4 (mod 16) doubles => conflict-free 8x4 / 4x8 fragment reads
 
@@ -49,43 +50,101 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 }
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
+  // not volatile: the scheduler may interleave the k-loop's cp.async address arithmetic with the MMAs
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
 }
 
-// Copy a (rows x cols) tile of a row-major matrix (pitch ld, extent R x C) starting at
-// (r0, c0) into shared memory, 16 bytes (2 doubles) per cp.async, zero-filling out of range.
-// Requires ld even and a 16-byte aligned base so every in-range chunk is aligned.
-template <int ROWS, int COLS, int PITCH>
-__device__ __forceinline__ void load_tile(double* smem, const double* __restrict__ g, int64_t ld,
-                                          int64_t R, int64_t C, int64_t r0, int64_t c0) {
-  constexpr int kChunksPerRow = COLS / 2;
-  constexpr int kChunks = ROWS * kChunksPerRow;
-  static_assert(kChunks % kGemmThreads == 0, "tile must divide evenly over the CTA");
+// Streams (ROWS x COLS) tiles of a row-major matrix into shared memory, 16 bytes per cp.async,
+// zero-filling everything out of range.  One of the two tile axes is the contraction axis and
+// advances by BK per k-tile (K_IS_ROW: tile rows run along k); the other is fixed for the CTA.
+// All per-thread addressing is precomputed once per term, so a k-tile costs one pointer bump,
+// one byte-count and ITERS cp.async per thread.  Requires an even pitch and a 16-byte aligned
+// base so that every in-range chunk is aligned.
+template <int ROWS, int COLS, int PITCH, bool K_IS_ROW>
+struct TileLoader {
+  static constexpr int kChunksPerRow = COLS / 2;
+  static constexpr int kRowStep = kGemmThreads / kChunksPerRow;  // tile rows covered per sweep
+  static constexpr int ITERS = ROWS / kRowStep;
+  static_assert(kGemmThreads % kChunksPerRow == 0 && ROWS % kRowStep == 0, "tile must divide evenly over the CTA");
+
+  const double* ptr;   // element (r_base, c) of the current tile
+  int64_t sweep;       // kRowStep * ld
+  int64_t k_step;      // pointer bump per k-tile
+  int smem_off;
+  int r_base, c;
+  uint32_t fixed_ok;   // K_IS_ROW: 0/8/16 bytes valid along the fixed (column) axis; else row-valid bit mask
+
+  __device__ __forceinline__ void init(const double* src, int64_t ld, int64_t fixed0, int64_t fixed_max, int64_t k0) {
+    r_base = threadIdx.x / kChunksPerRow;
+    c = (threadIdx.x % kChunksPerRow) * 2;
+    smem_off = r_base * PITCH + c;
+    sweep = (int64_t)kRowStep * ld;
+    if (K_IS_ROW) {
+      const int64_t gc = fixed0 + c;
+      fixed_ok = gc + 1 < fixed_max ? 16u : (gc < fixed_max ? 8u : 0u);
+      ptr = src + (k0 + r_base) * ld + (fixed_ok ? gc : 0);
+      k_step = (int64_t)BK * ld;
+    } else {
+      fixed_ok = 0;
 #pragma unroll
-  for (int it = 0; it < kChunks / kGemmThreads; ++it) {
-    const int chunk = it * kGemmThreads + threadIdx.x;
-    const int r = chunk / kChunksPerRow, c = (chunk % kChunksPerRow) * 2;
-    const int64_t gr = r0 + r, gc = c0 + c;
-    int bytes = 0;
-    if (gr < R && gc < C) bytes = (gc + 1 < C) ? 16 : 8;
-    // keep the address in range even when nothing is read
-    const double* src = bytes ? g + gr * ld + gc : g;
-    cp_async16(smem + r * PITCH + c, src, bytes);
+      for (int it = 0; it < ITERS; ++it)
+        if (fixed0 + r_base + it * kRowStep < fixed_max) fixed_ok |= 1u << it;
+      ptr = src + (fixed0 + r_base) * ld + k0 + c;
+      k_step = BK;
+    }
   }
-}
+  // One of the ITERS cp.async of a tile (k_left = k_hi - k_cur: valid contraction indices from the
+  // start of this tile).  The pieces are issued between the MMA steps of the previous tile so
+  // that their issue cost hides behind the other warp's DMMA stream.
+  __device__ __forceinline__ void load_piece(double* smem, int it, int64_t k_left, const double* safe) {
+    double* dst = smem + smem_off + it * kRowStep * PITCH;
+    int bytes;
+    if (K_IS_ROW) {
+      bytes = (r_base + it * kRowStep < k_left) ? (int)fixed_ok : 0;
+    } else {
+      const int64_t left = k_left - c;
+      const int col_bytes = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+      bytes = ((fixed_ok >> it) & 1u) ? col_bytes : 0;
+    }
+    cp_async16(dst, bytes ? ptr + it * sweep : safe, bytes);
+  }
+  __device__ __forceinline__ void advance() { ptr += k_step; }
+  __device__ __forceinline__ void load(double* smem, int64_t k_left, const double* safe) {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) load_piece(smem, it, k_left, safe);
+    advance();
+  }
+};
 
-struct GemmParams {
+// One contraction term: C += op(A)[M x K] . op(B)[K x N].
+struct GemmTerm {
   const double* A;
   const double* B;
-  const double* Cin;  // optional addend (may alias C)
+  int64_t lda, ldb, K;
+};
+// One output block: C = Cin + sum over `term_count` terms (the k-chain of BlockArray._tensordot,
+// blockarray.py:460-472, accumulated in registers instead of through `add` kernels).
+struct GemmProblem {
   double* C;
-  int64_t M, N, K;
-  int64_t lda, ldb, ldc, ldcin;
-  int64_t k_per_split;   // multiple of BK
+  const double* Cin;  // optional addend (may alias C)
+  int64_t ldc, ldcin, M, N;
+  int32_t tiles_m, tiles_n;
+  int32_t term_begin, term_count;
+  int32_t tile_begin;  // first CTA index of this problem
+  int32_t pad_;
+};
+
+struct GemmParams {
+  GemmProblem single;           // used when nproblems == 1 (no table upload)
+  GemmTerm single_term;
+  const GemmProblem* problems;  // device tables when nproblems > 1 or term_count > 1
+  const GemmTerm* terms;
+  int32_t nproblems;
+  int32_t use_table;
+  int64_t k_per_split;   // split-K (single problem, single term only); multiple of BK
   int64_t split_stride;  // elements between split-K partial outputs (M*N) or 0
-  int tiles_m, tiles_n;
 };
 
 template <bool TA, bool TB>
@@ -97,22 +156,31 @@ dgemm_dmma_kernel(GemmParams p) {
   double* sA = smem;
   double* sB = smem + kStages * AT::doubles;
 
-  // Tile order: groups of 8 tile-rows sweep the columns, so concurrently running CTAs share
-  // A row panels and B column panels in L2.
-  int tile = blockIdx.x;
+  // ---- which problem / tile does this CTA own? ---------------------------------------------------
+  GemmProblem prob;
+  if (p.use_table) {
+    int lo = 0, hi = p.nproblems - 1;
+    while (lo < hi) {  // last problem whose tile_begin <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (p.problems[mid].tile_begin <= (int)blockIdx.x) lo = mid;
+      else hi = mid - 1;
+    }
+    prob = p.problems[lo];
+  } else {
+    prob = p.single;
+  }
+  // Tile order inside a problem: groups of 8 tile-rows sweep the columns, so concurrently running
+  // CTAs share A row panels and B column panels in L2.
+  const int tile = (int)blockIdx.x - prob.tile_begin;
   constexpr int kGroup = 8;
-  const int tiles_per_group = kGroup * p.tiles_n;
+  const int tiles_per_group = kGroup * prob.tiles_n;
   const int group = tile / tiles_per_group;
   const int first_m = group * kGroup;
-  const int group_rows = min(p.tiles_m - first_m, kGroup);
+  const int group_rows = min(prob.tiles_m - first_m, kGroup);
   const int tm = first_m + (tile % tiles_per_group) % group_rows;
   const int tn = (tile % tiles_per_group) / group_rows;
   const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
-
-  const int64_t k_begin = (int64_t)blockIdx.z * p.k_per_split;
-  int64_t k_end = k_begin + p.k_per_split;
-  if (k_end > p.K) k_end = p.K;
-  const int KT = (int)((k_end - k_begin + BK - 1) / BK);
+  const int64_t M = prob.M, N = prob.N;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 3) * 32;   // 4 warps along M
@@ -125,34 +193,84 @@ dgemm_dmma_kernel(GemmParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  auto load_stage = [&](int slot, int kt) {
-    const int64_t k0 = k_begin + (int64_t)kt * BK;
-    double* a = sA + slot * AT::doubles;
-    double* b = sB + slot * BT::doubles;
-    if (TA) load_tile<BK, BM, AT::pitch>(a, p.A, p.lda, k_end, p.M, k0, m0);
-    else load_tile<BM, BK, AT::pitch>(a, p.A, p.lda, p.M, k_end, m0, k0);
-    if (TB) load_tile<BN, BK, BT::pitch>(b, p.B, p.ldb, p.N, k_end, n0, k0);
-    else load_tile<BK, BN, BT::pitch>(b, p.B, p.ldb, k_end, p.N, k0, n0);
+  // ---- producer cursor over (term, k-tile) -----------------------------------------------------------
+  int term_idx = 0;
+  GemmTerm term = p.use_table ? p.terms[prob.term_begin] : p.single_term;
+  int64_t k_lo = 0, k_hi = term.K;
+  if (p.k_per_split > 0) {  // split-K slice of a single-term problem
+    k_lo = (int64_t)blockIdx.z * p.k_per_split;
+    k_hi = k_lo + p.k_per_split;
+    if (k_hi > term.K) k_hi = term.K;
+  }
+  int64_t k_cur = k_lo;
+  // total number of k-tiles this CTA will consume
+  int KT = 0;
+  if (p.use_table) {
+    for (int s = 0; s < prob.term_count; ++s)
+      KT += (int)((p.terms[prob.term_begin + s].K + BK - 1) / BK);
+  } else {
+    KT = (int)((k_hi - k_lo + BK - 1) / BK);
+  }
+
+  // A tile: "N" storage (m, k) -> rows fixed, k along columns; "T" storage (k, m) -> k along rows.
+  TileLoader<AT::rows, AT::cols, AT::pitch, TA> la;
+  // B tile: "N" storage (k, n) -> k along rows; "T" storage (n, k) -> k along columns.
+  TileLoader<BT::rows, BT::cols, BT::pitch, !TB> lb;
+  la.init(term.A, term.lda, m0, M, k_cur);
+  lb.init(term.B, term.ldb, n0, N, k_cur);
+
+  auto finish_tile = [&]() {   // after all pieces of one k-tile have been issued
+    la.advance();
+    lb.advance();
+    k_cur += BK;
+    if (k_cur >= k_hi && term_idx + 1 < prob.term_count) {  // advance to the next term of the chain
+      ++term_idx;
+      term = p.terms[prob.term_begin + term_idx];
+      k_cur = 0;
+      k_hi = term.K;
+      la.init(term.A, term.lda, m0, M, 0);
+      lb.init(term.B, term.ldb, n0, N, 0);
+    }
   };
+  using LA = decltype(la);
+  using LB = decltype(lb);
+  static_assert(LA::ITERS == BK / 4 && LB::ITERS == BK / 4, "one A piece and one B piece per MMA k-step");
 
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
-    if (s < KT) load_stage(s, s);
+    if (s < KT) {
+      la.load(sA + s * AT::doubles, k_hi - k_cur, term.A);
+      lb.load(sB + s * BT::doubles, k_hi - k_cur, term.B);
+      // load() already advanced the pointers
+      k_cur += BK;
+      if (k_cur >= k_hi && term_idx + 1 < prob.term_count) {
+        ++term_idx;
+        term = p.terms[prob.term_begin + term_idx];
+        k_cur = 0;
+        k_hi = term.K;
+        la.init(term.A, term.lda, m0, M, 0);
+        lb.init(term.B, term.ldb, n0, N, 0);
+      }
+    }
     cp_async_commit();
   }
 
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<kStages - 2>();
     __syncthreads();
-    {
-      const int next = kt + kStages - 1;
-      if (next < KT) load_stage(next % kStages, next);
-      cp_async_commit();
-    }
+    const int next = kt + kStages - 1;
+    const bool prefetch = next < KT;
+    double* na = sA + (next % kStages) * AT::doubles;
+    double* nb = sB + (next % kStages) * BT::doubles;
+    const int64_t k_left = k_hi - k_cur;
     const double* a = sA + (kt % kStages) * AT::doubles;
     const double* b = sB + (kt % kStages) * BT::doubles;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
+      if (prefetch) {   // slot `next` was consumed in iteration kt - 1: free after the barrier above
+        la.load_piece(na, kk / 4, k_left, term.A);
+        lb.load_piece(nb, kk / 4, k_left, term.B);
+      }
       double af[4], bf[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -169,27 +287,29 @@ dgemm_dmma_kernel(GemmParams p) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) dmma884(acc[i][j], af[i], bf[j]);
     }
+    if (prefetch) finish_tile();
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
   // Epilogue: lane (g, t) owns C[m = 8i + g][n = 8j + 2t, 2t + 1].
-  double* out = p.C + (int64_t)blockIdx.z * p.split_stride;
-  const bool vec_ok = (p.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+  double* out = prob.C + (int64_t)blockIdx.z * p.split_stride;
+  const bool vec_ok = (prob.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t m = m0 + wm + i * 8 + g;
-    if (m >= p.M) continue;
+    if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int64_t n = n0 + wn + j * 8 + 2 * t;
-      if (n >= p.N) continue;
+      if (n >= N) continue;
       double v0 = acc[i][j][0], v1 = acc[i][j][1];
-      if (p.Cin != nullptr) {
-        v0 += p.Cin[m * p.ldcin + n];
-        if (n + 1 < p.N) v1 += p.Cin[m * p.ldcin + n + 1];
+      if (prob.Cin != nullptr) {
+        v0 += prob.Cin[m * prob.ldcin + n];
+        if (n + 1 < N) v1 += prob.Cin[m * prob.ldcin + n + 1];
       }
-      double* dst = out + m * p.ldc + n;
-      if (n + 1 < p.N) {
+      double* dst = out + m * prob.ldc + n;
+      if (n + 1 < N) {
         if (vec_ok) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
         else {
           dst[0] = v0;
@@ -502,26 +622,38 @@ int run_dot(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, const
 }
 
 template <bool TA, bool TB>
-int launch_dmma(const GemmParams& p, int splits, cudaStream_t s) {
+int launch_dmma(const GemmParams& p, unsigned tiles, int splits, cudaStream_t s) {
   const size_t smem = (size_t)kStages * (ATile<TA>::doubles + BTile<TB>::doubles) * sizeof(double);
   NUMS_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), 1, (unsigned)splits);
+  dim3 grid(tiles, 1, (unsigned)splits);
   dgemm_dmma_kernel<TA, TB><<<grid, kGemmThreads, smem, s>>>(p);
   NUMS_LAUNCH_OK();
   return NUMS_OK;
+}
+
+int dispatch_dmma(int ta, int tb, const GemmParams& p, unsigned tiles, int splits, cudaStream_t s) {
+  if (ta && tb) return launch_dmma<true, true>(p, tiles, splits, s);
+  if (ta) return launch_dmma<true, false>(p, tiles, splits, s);
+  if (tb) return launch_dmma<false, true>(p, tiles, splits, s);
+  return launch_dmma<false, false>(p, tiles, splits, s);
 }
 
 int run_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
               int64_t ldb, const double* Cin, int64_t ldcin, double* C, int64_t ldc, void* ws,
               size_t ws_bytes, cudaStream_t s) {
   GemmParams p;
-  p.A = A; p.B = B; p.Cin = Cin; p.C = C;
-  p.M = M; p.N = N; p.K = K;
-  p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldcin = ldcin;
-  p.tiles_m = (int)ceil_div(M, BM);
-  p.tiles_n = (int)ceil_div(N, BN);
-  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
+  memset(&p, 0, sizeof(p));
+  p.single.C = C; p.single.Cin = Cin; p.single.ldc = ldc; p.single.ldcin = ldcin;
+  p.single.M = M; p.single.N = N;
+  p.single.tiles_m = (int)ceil_div(M, BM);
+  p.single.tiles_n = (int)ceil_div(N, BN);
+  p.single.term_begin = 0; p.single.term_count = 1; p.single.tile_begin = 0;
+  p.single_term.A = A; p.single_term.B = B; p.single_term.lda = lda; p.single_term.ldb = ldb; p.single_term.K = K;
+  p.nproblems = 1;
+  p.use_table = 0;
+  const int64_t tiles = (int64_t)p.single.tiles_m * p.single.tiles_n;
+  NUMS_REQUIRE(tiles < 0x7fffffffLL, "gemm: too many output tiles");
   const int sms = sm_count();
   // Split K when the output has too few tiles to fill the machine and K is long.
   int splits = 1;
@@ -532,30 +664,32 @@ int run_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, const double* A, 
     if (splits > 1024) splits = 1024;
     if (splits < 1) splits = 1;
   }
-  int64_t k_per_split = ceil_div(ceil_div(K, splits), BK) * BK;
-  splits = (int)ceil_div(K, k_per_split);
-  p.k_per_split = k_per_split;
-  p.split_stride = 0;
+  if (splits > 1) {
+    const int64_t k_per_split = ceil_div(ceil_div(K, splits), BK) * BK;
+    splits = (int)ceil_div(K, k_per_split);
+    p.k_per_split = k_per_split;
+  }
   if (splits > 1) {
     const size_t need = (size_t)splits * M * N * sizeof(double);
     NUMS_NEED_WS(need, ws_bytes);
-    p.C = static_cast<double*>(ws);
-    p.ldc = N;
-    p.Cin = nullptr;
+    p.single.C = static_cast<double*>(ws);
+    p.single.ldc = N;
+    p.single.Cin = nullptr;
     p.split_stride = M * N;
+  } else {
+    p.k_per_split = 0;
   }
-  int rc;
-  if (ta && tb) rc = launch_dmma<true, true>(p, splits, s);
-  else if (ta) rc = launch_dmma<true, false>(p, splits, s);
-  else if (tb) rc = launch_dmma<false, true>(p, splits, s);
-  else rc = launch_dmma<false, false>(p, splits, s);
-  if (rc) return rc;
+  if (int rc = dispatch_dmma(ta, tb, p, (unsigned)tiles, splits, s)) return rc;
   if (splits > 1) {
     splitk_fold_kernel<<<blocks_for(M * N, 256, (int64_t)sms * 8), 256, 0, s>>>(
         static_cast<const double*>(ws), splits, M, N, Cin, ldcin, C, ldc);
     NUMS_LAUNCH_OK();
   }
   return NUMS_OK;
+}
+
+bool dmma_operand_ok(const void* ptr, int64_t ld) {
+  return (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0);
 }
 
 template <typename T>
@@ -578,9 +712,7 @@ int run_gemm_typed(int ta, int tb, int64_t M, int64_t N, int64_t K, const T* A, 
     return run_gemv_t<T>(B, ldb, K, N, A, inca, Cin, C, 1, ws, ws_bytes, s);
   }
   if constexpr (std::is_same<T, double>::value) {
-    const bool aligned = (lda % 2 == 0) && (ldb % 2 == 0) &&
-                         ((reinterpret_cast<uintptr_t>(A) & 15u) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(B) & 15u) == 0);
+    const bool aligned = dmma_operand_ok(A, lda) && dmma_operand_ok(B, ldb);
     const bool worthwhile = M * N >= 32 * 32 || K >= 4096;
     if (aligned && worthwhile)
       return run_dgemm(ta, tb, M, N, K, A, lda, B, ldb, Cin, ldc, C, ldc, ws, ws_bytes, s);
@@ -631,4 +763,58 @@ extern "C" int nums_gemm(int dtype, int trans_a, int trans_b, int64_t m, int64_t
                                      accumulate, ws, ws_bytes, s);
   }
   NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "gemm: dtype %s", dtype_name(dtype));
+}
+
+extern "C" int nums_gemm_grouped(int dtype, int trans_a, int trans_b, int nproblems,
+                                 const nums_gemm_problem_t* problems_host, int nterms,
+                                 const nums_gemm_term_t* terms_host, void* ws, size_t ws_bytes,
+                                 void* stream) {
+  using namespace nums;
+  NUMS_REQUIRE(dtype == NUMS_F64, "gemm_grouped: float64 only (dtype %s)", dtype_name(dtype));
+  NUMS_REQUIRE(nproblems >= 1 && nterms >= nproblems && problems_host && terms_host, "gemm_grouped: empty group");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t prob_bytes = ((size_t)nproblems * sizeof(GemmProblem) + 255) & ~(size_t)255;
+  const size_t term_bytes = (size_t)nterms * sizeof(GemmTerm);
+  NUMS_NEED_WS(prob_bytes + term_bytes, ws_bytes);
+  std::vector<GemmProblem> probs((size_t)nproblems);
+  std::vector<GemmTerm> terms((size_t)nterms);
+  int64_t tile_cursor = 0;
+  for (int i = 0; i < nproblems; ++i) {
+    const nums_gemm_problem_t& src = problems_host[i];
+    NUMS_REQUIRE(src.m >= 1 && src.n >= 1 && src.C != nullptr, "gemm_grouped: problem %d is empty", i);
+    NUMS_REQUIRE(src.term_count >= 1 && src.term_begin >= 0 && src.term_begin + src.term_count <= nterms,
+                 "gemm_grouped: problem %d has a bad term range", i);
+    GemmProblem& d = probs[(size_t)i];
+    d.C = static_cast<double*>(src.C);
+    d.Cin = static_cast<const double*>(src.Cin);
+    d.ldc = src.ldc; d.ldcin = src.ldcin; d.M = src.m; d.N = src.n;
+    d.tiles_m = (int)ceil_div(src.m, BM);
+    d.tiles_n = (int)ceil_div(src.n, BN);
+    d.term_begin = src.term_begin; d.term_count = src.term_count;
+    d.tile_begin = (int)tile_cursor;
+    d.pad_ = 0;
+    tile_cursor += (int64_t)d.tiles_m * d.tiles_n;
+    NUMS_REQUIRE(tile_cursor < 0x7fffffffLL, "gemm_grouped: too many tiles");
+  }
+  for (int i = 0; i < nterms; ++i) {
+    const nums_gemm_term_t& src = terms_host[i];
+    NUMS_REQUIRE(src.k >= 1 && src.A && src.B, "gemm_grouped: term %d is empty", i);
+    NUMS_REQUIRE(dmma_operand_ok(src.A, src.lda) && dmma_operand_ok(src.B, src.ldb),
+                 "gemm_grouped: term %d is not 16-byte aligned with even pitches", i);
+    GemmTerm& d = terms[(size_t)i];
+    d.A = static_cast<const double*>(src.A);
+    d.B = static_cast<const double*>(src.B);
+    d.lda = src.lda; d.ldb = src.ldb; d.K = src.k;
+  }
+  char* base = static_cast<char*>(ws);
+  // pageable sources: the runtime stages them before returning, so the vectors may die here
+  NUMS_CUDA_OK(cudaMemcpyAsync(base, probs.data(), (size_t)nproblems * sizeof(GemmProblem), cudaMemcpyHostToDevice, s));
+  NUMS_CUDA_OK(cudaMemcpyAsync(base + prob_bytes, terms.data(), term_bytes, cudaMemcpyHostToDevice, s));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.problems = reinterpret_cast<const GemmProblem*>(base);
+  p.terms = reinterpret_cast<const GemmTerm*>(base + prob_bytes);
+  p.nproblems = nproblems;
+  p.use_table = 1;
+  return dispatch_dmma(trans_a, trans_b, p, (unsigned)tile_cursor, 1, s);
 }

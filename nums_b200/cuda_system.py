@@ -22,6 +22,9 @@ import numpy as np
 import torch
 
 from nums_b200 import cuda_compute
+from nums_b200.deferred import ContractionQueue, DeferredContraction
+
+_BOP_PARAMS = ("op", "a1", "a2", "a1_shape", "a2_shape", "a1_T", "a2_T", "axes")
 
 
 class CudaSystem(object):
@@ -41,6 +44,8 @@ class CudaSystem(object):
         self.placement = placement
         self._device = device
         self._imp = None
+        # float64 tensordot / add chains are deferred and run as one grouped launch (deferred.py)
+        self.contractions = ContractionQueue()
 
     # -- lifecycle ---------------------------------------------------------------------------
     def init(self):
@@ -77,6 +82,7 @@ class CudaSystem(object):
         return cuda_compute.upload(value)
 
     def get(self, object_ids):
+        object_ids = self.contractions.resolve(object_ids)
         if isinstance(object_ids, (list, tuple)):
             return type(object_ids)(self.get(o) for o in object_ids) if isinstance(object_ids, tuple) \
                 else [self.get(o) for o in object_ids]
@@ -101,7 +107,34 @@ class CudaSystem(object):
     def call(self, name, *args, **kwargs):
         kwargs = dict(kwargs)
         kwargs.pop("syskwargs", None)
+        q = self.contractions
+        if name == "bop" and q.enabled:
+            lazy = self._try_defer(args, kwargs)
+            if lazy is not None:
+                return lazy
+        args = tuple(q.resolve(a) for a in args)
+        kwargs = {k: q.resolve(v) for k, v in kwargs.items()}
         return self.remote_functions[name](*args, **kwargs)
+
+    def _try_defer(self, args, kwargs):
+        """tensordot -> DeferredContraction; add of deferred contractions -> longer term list."""
+        bound = dict(zip(_BOP_PARAMS, args))
+        bound.update(kwargs)
+        if len(bound) != len(_BOP_PARAMS):
+            return None
+        op, a1, a2 = bound["op"], bound["a1"], bound["a2"]
+        q = self.contractions
+        if op == "tensordot":
+            if isinstance(a1, DeferredContraction) or isinstance(a2, DeferredContraction):
+                return None
+            return q.tensordot(a1, a2, bound["a1_shape"], bound["a2_shape"], bound["a1_T"], bound["a2_T"], bound["axes"])
+        if op == "add" and (isinstance(a1, DeferredContraction) or isinstance(a2, DeferredContraction)):
+            return q.add(a1, a2, bound["a1_shape"], bound["a2_shape"], bound["a1_T"], bound["a2_T"])
+        return None
+
+    def flush(self):
+        """Launch every deferred contraction now (used between SUMMA steps)."""
+        self.contractions.flush()
 
     def call_with_options(self, name, args, kwargs, options):
         return self.call(name, *args, **kwargs)
@@ -125,4 +158,5 @@ class CudaSystem(object):
         return int(np.ravel_multi_index(tuple(coords), dg))
 
     def synchronize(self):
+        self.contractions.flush()
         torch.cuda.current_stream().synchronize()

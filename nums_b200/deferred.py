@@ -1,0 +1,150 @@
+"""Deferred block contractions: turning ``dot`` + ``add`` chains into one grouped DMMA launch.
+
+``BlockArray._tensordot`` (blockarray.py:460-472) computes every result block as
+``dot(A[i,0], B[0,j]); for k > 0: result_block += dot(A[i,k], B[k,j])`` -- 512 ``tensordot`` and
+448 ``add`` kernel calls for an 8 x 8 grid, each ``add`` a full read-read-write pass over a result
+block and each 2048^2 ``tensordot`` 1.73 waves on 148 SMs.  Blocks are immutable in NumS, so
+``CudaSystem`` may postpone the arithmetic: a float64 ``tensordot`` returns a
+``DeferredContraction`` (a list of (A, B) terms), ``add`` of deferred contractions concatenates the
+term lists, and the first call that needs actual data (``touch``, ``get``, any other kernel)
+flushes *all* outstanding contractions through ``nums_gemm_grouped``: one launch whose CTAs walk
+the tiles of every result block and accumulate each block's whole k-chain in registers.  The
+unchanged host code therefore runs the blocked matmul as a single large GEMM.
+"""
+import weakref
+
+import numpy as np
+import torch
+
+from nums_b200 import _lib, cuda_compute
+from nums_b200._lib import LIB
+
+MIN_EXTENT = 64   # smaller outputs / vector forms run eagerly (GEMV / split-K kernels)
+
+
+GemmTerm, GemmProblem = _lib.GemmTerm, _lib.GemmProblem
+
+
+class DeferredContraction(object):
+    """value = addend + sum_t op(A_t) . op(B_t); materialised by ``ContractionQueue.flush``."""
+    __slots__ = ("terms", "addend", "shape", "flags", "value", "__weakref__")
+
+    def __init__(self, terms, shape, flags, addend=None):
+        self.terms = terms        # tuple of (A tensor, lda, B tensor, ldb, k)
+        self.shape = shape        # (m, n)
+        self.flags = flags        # (trans_a, trans_b), shared by all terms
+        self.addend = addend      # concrete (m, n) float64 tensor or None
+        self.value = None
+
+    @property
+    def dtype(self):
+        return torch.float64
+
+
+def _dmma_ok(t, ld):
+    return t.dtype == torch.float64 and t.data_ptr() % 16 == 0 and ld % 2 == 0
+
+
+class ContractionQueue(object):
+
+    def __init__(self):
+        self._pending = []   # weak references to unmaterialised contractions, in creation order
+        self.flushes = 0
+        self.enabled = True
+
+    # -- building -------------------------------------------------------------------------------
+    def tensordot(self, a1, a2, a1_shape, a2_shape, a1_T, a2_T, axes):
+        """Deferred np.tensordot(a1, a2, axes=1) for 2-D float64 operands, or None if ineligible."""
+        if not self.enabled or axes != 1 or len(a1_shape) != 2 or len(a2_shape) != 2:
+            return None
+        if not (isinstance(a1, torch.Tensor) and isinstance(a2, torch.Tensor)):
+            return None
+        if a1.dtype != torch.float64 or a2.dtype != torch.float64:
+            return None
+        m, k = int(a1_shape[0]), int(a1_shape[1])
+        k2, n = int(a2_shape[0]), int(a2_shape[1])
+        if k != k2 or m < MIN_EXTENT or n < MIN_EXTENT or k < 1:
+            return None
+        x = cuda_compute._operand(a1, a1_shape, a1_T)
+        y = cuda_compute._operand(a2, a2_shape, a2_T)
+        A, ta, lda = cuda_compute._as_matrix(x, m, k)
+        B, tb, ldb = cuda_compute._as_matrix(y, k, n)
+        if not (_dmma_ok(A, lda) and _dmma_ok(B, ldb)):
+            return None
+        return self._register(DeferredContraction(((A, lda, B, ldb, k),), (m, n), (bool(ta), bool(tb))))
+
+    def add(self, x, y, x_shape, y_shape, x_T, y_T):
+        """Lazy x + y when at least one side is an unmaterialised contraction of the same shape."""
+        dx = isinstance(x, DeferredContraction) and x.value is None
+        dy = isinstance(y, DeferredContraction) and y.value is None
+        if not (dx or dy) or x_T or y_T or tuple(x_shape) != tuple(y_shape):
+            return None
+        if dx and dy:
+            if x.flags != y.flags or (x.addend is not None and y.addend is not None):
+                return None
+            addend = x.addend if x.addend is not None else y.addend
+            return self._register(DeferredContraction(x.terms + y.terms, x.shape, x.flags, addend))
+        lazy, other = (x, y) if dx else (y, x)
+        if isinstance(other, DeferredContraction):
+            other = other.value
+        if (not isinstance(other, torch.Tensor) or other.dtype != torch.float64 or lazy.addend is not None
+                or tuple(other.shape) != tuple(lazy.shape) or not other.is_contiguous()):
+            return None
+        return self._register(DeferredContraction(lazy.terms, lazy.shape, lazy.flags, other))
+
+    def _register(self, d):
+        self._pending.append(weakref.ref(d))
+        return d
+
+    # -- materialising ----------------------------------------------------------------------------
+    def resolve(self, obj):
+        """Replace deferred contractions (also inside lists / tuples) by concrete tensors."""
+        if isinstance(obj, DeferredContraction):
+            if obj.value is None:
+                self.flush()
+            return obj.value
+        if isinstance(obj, list):
+            return [self.resolve(o) for o in obj]
+        if isinstance(obj, tuple) and any(isinstance(o, DeferredContraction) for o in obj):
+            return tuple(self.resolve(o) for o in obj)
+        return obj
+
+    def flush(self):
+        """One grouped launch per (trans_a, trans_b) class for everything still referenced."""
+        alive = []
+        for ref in self._pending:
+            d = ref()
+            if d is not None and d.value is None:
+                alive.append(d)
+        self._pending = []
+        if not alive:
+            return
+        self.flushes += 1
+        by_flags = {}
+        for d in alive:
+            by_flags.setdefault(d.flags, []).append(d)
+        stream = cuda_compute._stream()
+        for (ta, tb), group in by_flags.items():
+            nterms = sum(len(d.terms) for d in group)
+            problems = (GemmProblem * len(group))()
+            terms = (GemmTerm * nterms)()
+            cursor = 0
+            for i, d in enumerate(group):
+                m, n = d.shape
+                out = cuda_compute._empty((m, n), np.float64)
+                d.value = out
+                pr = problems[i]
+                pr.C = out.data_ptr()
+                pr.Cin = d.addend.data_ptr() if d.addend is not None else None
+                pr.ldc, pr.ldcin, pr.m, pr.n = n, n, m, n
+                pr.term_begin, pr.term_count = cursor, len(d.terms)
+                for (A, lda, B, ldb, k) in d.terms:
+                    tm = terms[cursor]
+                    tm.A, tm.B, tm.lda, tm.ldb, tm.k = A.data_ptr(), B.data_ptr(), lda, ldb, k
+                    cursor += 1
+            device = group[0].value.device
+            LIB.call_ws(LIB.dll.nums_gemm_grouped, device,
+                        ((_lib.F64, int(ta), int(tb), len(group), problems, nterms, terms), (stream,)))
+            for d in group:      # operands may be released now; the stream keeps the ordering
+                d.terms = ()
+                d.addend = None

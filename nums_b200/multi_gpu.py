@@ -168,6 +168,8 @@ class SummaMatmul(object):
                     prev = c_blocks.get((i, j))
                     c_blocks[(i, j)] = dot if prev is None else self.system.bop(
                         "add", prev, dot, shape, shape, False, False, axes=None, syskwargs=sysk)
+            if hasattr(self.system, "flush"):
+                self.system.flush()   # one grouped launch for this step's C += A(:,k) B(k,:) updates
         return c_blocks
 
 

@@ -1,0 +1,35 @@
+"""Tiny driver for ncu captures: launches each hot kernel a few times (development aid)."""
+import sys, os
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nums_b200 import cuda_compute as cc
+from nums_b200.cuda_system import CudaSystem
+
+which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+system = CudaSystem(); system.init()
+dev = torch.device("cuda", 0)
+if which == "gemm":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    A = torch.randn((n, n), dtype=torch.float64, device=dev)
+    B = torch.randn((n, n), dtype=torch.float64, device=dev)
+    for _ in range(4):
+        C = system.bop("tensordot", A, B, (n, n), (n, n), False, False, axes=1, syskwargs={})
+elif which == "bop":
+    n = 100_000_000
+    u = torch.rand(n, dtype=torch.float64, device=dev); v = torch.rand(n, dtype=torch.float64, device=dev)
+    for _ in range(4):
+        w = system.bop("add", u, v, (n,), (n,), False, False, axes=None, syskwargs={})
+elif which == "lr":
+    n, d = 11_000_000, 28
+    X = torch.randn((n, d), dtype=torch.float64, device=dev)
+    y = (torch.rand(n, device=dev) < 0.5).to(torch.float64)
+    beta = torch.randn(d, dtype=torch.float64, device=dev) / 5
+    for _ in range(4):
+        out = cc.lr_grad_hess(X, y, beta)
+elif which == "qr":
+    X = torch.randn((262144, 128), dtype=torch.float64, device=dev)
+    for _ in range(2):
+        r = cc.qr_r(X)
+torch.cuda.synchronize()
+print("done", which)

@@ -588,3 +588,41 @@ def test_lr_grad_hess(cuda_system, nd):
     assert rel_fro(out[:d], g) <= GEMM_TOL
     assert rel_fro(out[d:].reshape(d, d), H) <= GEMM_TOL
     assert np.array_equal(out[d:].reshape(d, d), out[d:].reshape(d, d).T)
+
+
+# ----------------------------------------------------------------------------------------------------
+# deferred dot/add chains (nums_b200/deferred.py): same results as the eager kernels and the oracle
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shapes", [((512, 384), (384, 640), (128, 128), (128, 128)),
+                                     ((300, 260), (260, 280), (128, 128), (128, 128)),
+                                     ((256, 1024), (1024, 192), (128, 256), (256, 64)),
+                                     ((130, 70), (70, 200), (66, 16), (16, 100))])
+def test_deferred_blocked_matmul(cuda_system, shapes):
+    from nums_b200 import blocks
+    from nums_b200._lib import LIB
+    (sa, sb, ba, bb) = shapes
+    rng = np.random.default_rng(81)
+    A, B = rng.standard_normal(sa), rng.standard_normal(sb)
+    app = blocks.ArrayApp(cuda_system)
+    a, b = app.array(A, ba), app.array(B, bb)
+    want = A @ B
+    for label, (x, y, ref) in {"nn": (a, b, want), "tn": (app.array(np.ascontiguousarray(A.T), ba[::-1]).T, b, want),
+                               "nt": (a, app.array(np.ascontiguousarray(B.T), bb[::-1]).T, want)}.items():
+        cuda_system.contractions.enabled = True
+        before = LIB.dll.nums_launch_count()
+        lazy = (x @ y).get()
+        lazy_launches = LIB.dll.nums_launch_count() - before
+        cuda_system.contractions.enabled = False
+        try:
+            before = LIB.dll.nums_launch_count()
+            eager = (x @ y).get()
+            eager_launches = LIB.dll.nums_launch_count() - before
+        finally:
+            cuda_system.contractions.enabled = True
+        assert rel_fro(lazy, ref) <= GEMM_TOL, label
+        assert rel_fro(eager, ref) <= GEMM_TOL, label
+        assert lazy_launches <= eager_launches, (label, lazy_launches, eager_launches)
+    # a chain that mixes a concrete addend, deferred terms and a non-contraction consumer
+    c = (a @ b) + (a @ b)
+    d = c * 2.0
+    assert rel_fro(d.get(), 4.0 * want) <= GEMM_TOL
