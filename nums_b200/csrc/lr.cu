@@ -195,6 +195,203 @@ lr_grad_hess_kernel(const double* __restrict__ X, int64_t ldx, const double* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path: dense row blocks (ldx == d) with d == 4 or 12 (mod 16), e.g. the HIGGS shape d = 28.
+//
+// A 256-row tile of X is then one contiguous run of 256*d*8 bytes, so the whole tile is fetched by
+// ONE bulk asynchronous copy (cp.async.bulk.shared::cluster.global -> UBLKCP, the TMA engine)
+// issued by a single thread and tracked by an mbarrier -- no per-thread address arithmetic, no
+// LDGSTS issue slots.  With pitch d == 4 or 12 (mod 16) doubles the (row = t, feature = g)
+// fragment reads of the dense tile are bank-conflict free without padding.
+//   pass 1: lane l owns row l of the warp's 32 rows: z = x . beta with 128-bit shared loads,
+//           mu = sigmoid(z); s = mu (1 - mu) and e = mu - y go to a per-warp shared scratch;
+//   pass 2: 8 rank-4 updates; fragments straight from the tile, s / e broadcast-read from the
+//           scratch (no shuffles); H on the DMMA pipe (upper-triangular 8x8 blocks), g by DFMA.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+constexpr int kDenseStages = 3;
+
+template <int NB>
+__global__ void __launch_bounds__(kLrThreads, 1)
+lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                          const double* __restrict__ beta, int64_t n, int d, double* __restrict__ partial) {
+  constexpr int NTRI = NB * (NB + 1) / 2;
+  extern __shared__ __align__(128) unsigned char lr_smem[];
+  const int tile_doubles = kTileRows * d;
+  double* ring = reinterpret_cast<double*>(lr_smem);                       // kDenseStages tiles
+  double* scratch = ring + (size_t)kDenseStages * tile_doubles;            // 8 warps x (32 s + 32 e)
+  double* bsm = scratch + 8 * 64;                                          // beta, zero padded to NB*8
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + NB * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  for (int i = threadIdx.x; i < kDenseStages * tile_doubles; i += kLrThreads) ring[i] = 0.0;
+  for (int i = threadIdx.x; i < NB * 8; i += kLrThreads) bsm[i] = i < d ? beta[i] : 0.0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDenseStages; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  fence_proxy_async();   // the zero fill (generic proxy) happens-before the bulk copies (async proxy)
+  __syncthreads();
+
+  const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
+  auto issue = [&](int slot, int64_t tile) {   // one thread
+    const int64_t r0 = tile * kTileRows;
+    const int64_t rows = (n - r0 < kTileRows) ? (n - r0) : kTileRows;
+    const uint32_t bytes = (uint32_t)(rows * d * sizeof(double));
+    mbar_expect_tx(&bars[slot], bytes);
+    bulk_copy_g2s(ring + (size_t)slot * tile_doubles, X + r0 * d, bytes, &bars[slot]);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDenseStages - 1; ++s) {
+      const int64_t tl = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (tl < ntiles) issue(s, tl);
+    }
+  }
+
+  double hacc[NTRI][2];
+  double gacc[NB];
+#pragma unroll
+  for (int i = 0; i < NTRI; ++i) hacc[i][0] = hacc[i][1] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) gacc[i] = 0.0;
+  double* my_s = scratch + warp * 64;
+  double* my_e = my_s + 32;
+
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // every warp finished the tile that used the slot we are about to refill
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int64_t nxt = tile + (int64_t)(kDenseStages - 1) * gridDim.x;
+      int nslot = slot + kDenseStages - 1;
+      if (nslot >= kDenseStages) nslot -= kDenseStages;
+      if (nxt < ntiles) {
+        fence_proxy_async();
+        issue(nslot, nxt);
+      }
+    }
+    mbar_wait(&bars[slot], phase);
+    const double* xs = ring + (size_t)slot * tile_doubles + (size_t)warp * 32 * d;
+    const int64_t row0 = tile * kTileRows + warp * 32;
+
+    // pass 1: one row per lane
+    {
+      const double* xr = xs + lane * d;
+      double z0 = 0.0, z1 = 0.0;
+      for (int j = 0; j < d; j += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(xr + j);
+        z0 = fma(v.x, bsm[j], z0);
+        z1 = fma(v.y, bsm[j + 1], z1);
+      }
+      const int64_t myrow = row0 + lane;
+      const bool valid = myrow < n;
+      const double yv = valid ? y[myrow] : 0.0;
+      const double mu = 1.0 / (1.0 + exp(-(z0 + z1)));
+      my_s[lane] = valid ? mu * (1.0 - mu) : 0.0;   // rows past the end may hold stale data: weight 0
+      my_e[lane] = valid ? mu - yv : 0.0;
+    }
+    __syncwarp();
+
+    // pass 2: rank-4 updates
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const double s = my_s[4 * q + t];
+      const double e = my_e[4 * q + t];
+      const double* xr = xs + (4 * q + t) * d + g;
+      double xf[NB], af[NB];
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi) {
+        xf[bi] = (8 * bi + g < d) ? xr[8 * bi] : 0.0;
+        af[bi] = s * xf[bi];
+        gacc[bi] = fma(e, xf[bi], gacc[bi]);
+      }
+      int idx = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj) {
+          dmma884(hacc[idx], af[bi], xf[bj]);
+          ++idx;
+        }
+    }
+    __syncwarp();
+    ++slot;
+    if (slot == kDenseStages) {
+      slot = 0;
+      phase ^= 1u;
+    }
+  }
+  __syncthreads();
+
+  // ---- CTA fold through shared memory (reuses the ring) ----------------------------------------
+  constexpr int D8 = NB * 8;
+  constexpr int PER_WARP = D8 + D8 * D8;
+  double* red = ring;
+  for (int i = threadIdx.x; i < 8 * PER_WARP; i += kLrThreads) red[i] = 0.0;
+  __syncthreads();
+  double* mine = red + warp * PER_WARP;
+#pragma unroll
+  for (int bi = 0; bi < NB; ++bi) {
+    double v = gacc[bi];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (t == 0) mine[8 * bi + g] = v;
+  }
+  {
+    int idx = 0;
+#pragma unroll
+    for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+      for (int bj = bi; bj < NB; ++bj) {
+        double* h = mine + D8 + (8 * bi + g) * D8 + 8 * bj + 2 * t;
+        h[0] = hacc[idx][0];
+        h[1] = hacc[idx][1];
+        ++idx;
+      }
+  }
+  __syncthreads();
+  double* out = partial + (size_t)blockIdx.x * (d + d * d);
+  for (int i = threadIdx.x; i < d + d * d; i += kLrThreads) {
+    int src;
+    if (i < d) src = i;
+    else {
+      const int r = (i - d) / d, c = (i - d) - r * d;
+      src = (r <= c) ? D8 + r * D8 + c : D8 + c * D8 + r;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc += red[w * PER_WARP + src];
+    out[i] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 lr_fold_kernel(const double* __restrict__ partial, int parts, int len, double* __restrict__ out) {
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -205,9 +402,38 @@ lr_fold_kernel(const double* __restrict__ partial, int parts, int len, double* _
 }
 
 template <int NB>
+int launch_lr_dense(const double* X, const double* y, const double* beta, int64_t n, int d, double* out,
+                    void* ws, size_t ws_bytes, cudaStream_t s) {
+  const size_t tile_bytes = (size_t)kTileRows * d * sizeof(double);
+  const size_t smem = kDenseStages * tile_bytes + (8 * 64 + NB * 8) * sizeof(double) + kDenseStages * sizeof(uint64_t);
+  const int len = d + d * d;
+  const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
+  int grid = sm_count();
+  if (grid > ntiles) grid = (int)ntiles;
+  if (grid < 1) grid = 1;
+  NUMS_NEED_WS((size_t)grid * len * sizeof(double), ws_bytes);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(lr_grad_hess_dense_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lr_grad_hess_dense_kernel<NB><<<grid, kLrThreads, smem, s>>>(X, y, beta, n, d, static_cast<double*>(ws));
+  NUMS_LAUNCH_OK();
+  lr_fold_kernel<<<(len + 255) / 256, 256, 0, s>>>(static_cast<const double*>(ws), grid, len, out);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
+template <int NB>
 int launch_lr(const double* X, int64_t ldx, const double* y, const double* beta, int64_t n, int d,
               double* out, void* ws, size_t ws_bytes, cudaStream_t s) {
   constexpr int PITCH = lr_pitch(NB);
+  {
+    // dense fast path: contiguous rows whose pitch is conflict free as is, 3 tiles + scratch fit,
+    // and the per-CTA fold (8 x (D8 + D8^2) doubles) fits in the ring
+    const size_t tile_bytes = (size_t)kTileRows * d * sizeof(double);
+    const size_t smem = kDenseStages * tile_bytes + (8 * 64 + NB * 8 + 8) * sizeof(double);
+    const bool pitch_ok = (d % 16 == 4) || (d % 16 == 12);
+    if (ldx == d && pitch_ok && smem <= 227 * 1024 &&
+        (size_t)8 * (NB * 8 + NB * 8 * NB * 8) * sizeof(double) <= kDenseStages * tile_bytes)
+      return launch_lr_dense<NB>(X, y, beta, n, d, out, ws, ws_bytes, s);
+  }
   const size_t stage_bytes = (size_t)kTileRows * PITCH * sizeof(double);
   int stages = 3;
   if (3 * stage_bytes > 220 * 1024) stages = 2;

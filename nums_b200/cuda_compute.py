@@ -85,30 +85,56 @@ def _empty(shape, dtype):
 
 
 def upload(value, dtype=None):
-    """Host value -> device tensor (pinned staging, async H2D on the current stream)."""
+    """Host value -> device tensor on the current stream.
+
+    Page-locked sources (e.g. arrays backed by ``torch.empty(pin_memory=True)``) are copied
+    asynchronously straight from where they are; pageable ones go through the driver's own staging.
+    """
     if isinstance(value, torch.Tensor):
         return value
     arr = np.asarray(value) if dtype is None else np.asarray(value, dtype=dtype)
     _lib.dtype_code(arr.dtype)  # raises for unsupported dtypes
     if not arr.flags.c_contiguous:
         arr = np.ascontiguousarray(arr)
-    host = torch.from_numpy(arr.reshape(-1).copy() if arr.ndim == 0 else arr)
-    if host.numel() >= 1 << 16:
-        staged = torch.empty(host.shape, dtype=host.dtype, pin_memory=True)
-        staged.copy_(host)
-        out = staged.to(_device(), non_blocking=True)
-    else:
-        out = host.to(_device())
-    return out.view(tuple(arr.shape))
+    if arr.ndim == 0:
+        host = torch.from_numpy(arr.reshape(1).copy())
+        return host.to(_device()).view(())
+    if not arr.flags.writeable:
+        arr = arr.copy()
+    host = torch.from_numpy(arr)
+    big = host.numel() * host.element_size() >= (1 << 20)
+    return host.to(_device(), non_blocking=bool(big and host.is_pinned()))
+
+
+def _to_pinned(t):
+    """Start an asynchronous D2H copy into page-locked memory (torch's caching host allocator
+    recycles the buffers, so steady-state loops do not pay cudaHostAlloc)."""
+    if not t.is_contiguous():
+        t = _materialize(t)
+    host = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    return host
 
 
 def download(t):
     """Device tensor -> numpy array (synchronises the current stream)."""
     if not isinstance(t, torch.Tensor):
         return t
-    if not t.is_contiguous():
-        t = _materialize(t)
-    return t.cpu().numpy()
+    if t.numel() * t.element_size() < (1 << 16):
+        if not t.is_contiguous():
+            t = _materialize(t)
+        return t.cpu().numpy()
+    host = _to_pinned(t)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
+def download_many(tensors):
+    """Several device tensors -> numpy arrays with one synchronisation (BlockArray.get)."""
+    staged = [(_to_pinned(t) if isinstance(t, torch.Tensor) and t.numel() * t.element_size() >= (1 << 16) else None)
+              for t in tensors]
+    torch.cuda.current_stream().synchronize()
+    return [h.numpy() if h is not None else download(t) for h, t in zip(staged, tensors)]
 
 
 def _copy_into(dst, src):
@@ -588,8 +614,64 @@ def concatenate(arrs, axis):
     return out
 
 
-def qr_r(arr):
-    """R factor (k x n, k = min(m, n)) of a 2-D block: streaming Householder TSQR kernel."""
+# Tall-skinny fast path of qr_r: a block is factored through its Gram matrix (all DMMA GEMM work)
+# when a rigorous bound on its condition number says that is as accurate as Householder.
+QR_GRAM_MIN_ASPECT = 8        # m >= 8 n
+QR_GRAM_MAX_COLS = 256
+QR_GRAM_ACCEPT_KAPPA = 30.0   # one Cholesky pass: error ~ kappa^2 eps  (< 1e-12)
+QR_GRAM_REFINE_KAPPA = 1.0e6  # two passes (CholeskyQR2) are as good as Householder below ~1e7
+QR_STATS = {"gram": 0, "gram2": 0, "householder": 0}
+
+
+def _householder_r(arr):
+    m, n = arr.shape
+    r = _empty((min(m, n), n), _lib.numpy_dtype(arr.dtype))
+    LIB.call_ws(LIB.dll.nums_qr, arr.device,
+                ((_lib.dtype_code(arr.dtype), m, n, arr.data_ptr(), n, None, 0, r.data_ptr(), n), (_stream(),)))
+    QR_STATS["householder"] += 1
+    return r
+
+
+def _fro2(t):
+    """sum(t * t) as a 0-d device tensor (two tiny launches)."""
+    n = t.numel()
+    sq = _empty((n,), np.float64)
+    flat = t.view(n)
+    LIB.check(LIB.dll.nums_bop(_lib.BOP_CODE["multiply"], _lib.F64, describe(flat), describe(flat), describe(sq), _stream()))
+    out = _empty((), np.float64)
+    LIB.call_ws(LIB.dll.nums_reduce, t.device,
+                ((_lib.REDUCE_CODE["sum"], sq.data_ptr(), _lib.F64, 1, n, 1, out.data_ptr(), _lib.F64), (_stream(),)))
+    return out
+
+
+def _gram_factor(a):
+    """Cholesky factor L (lower) of a^T a, its inverse, and a rigorous bound on cond_2(a):
+    cond(a) = cond(L) <= ||L||_F ||L^-1||_F.  Returns (L, Linv, kappa_bound); kappa_bound is inf if
+    the Gram matrix is not numerically positive definite.  One 20-byte read-back."""
+    m, n = a.shape
+    gram = _empty((n, n), np.float64)
+    gemm_into(gram, a, True, n, a, False, n, n, n, m)
+    low = _empty((n, n), np.float64)
+    info = _empty((), np.int32)
+    LIB.call_ws(LIB.dll.nums_cholesky, a.device,
+                ((_lib.F64, n, gram.data_ptr(), n, low.data_ptr(), n, info.data_ptr()), (_stream(),)))
+    low_inv = _inv_nocheck(low)
+    stats = _empty((3,), np.float64)
+    _copy_into(stats[0], info)
+    _copy_into(stats[1], _fro2(low))
+    _copy_into(stats[2], _fro2(low_inv))
+    failed, n_l, n_li = (float(v) for v in stats.cpu())   # 24-byte D2H, the one sync of this path
+    if failed != 0 or not np.isfinite(n_l * n_li):
+        return low, low_inv, float("inf")
+    return low, low_inv, float(np.sqrt(n_l * n_li))
+
+
+def qr_r_ex(arr):
+    """(R, kappa_bound).  R is the k x n (k = min(m, n)) triangular factor of a 2-D block.
+
+    Tall float64 blocks go through the Gram matrix: R = chol(A^T A)^T when the condition bound is
+    tiny, CholeskyQR2 when it is moderate; everything else (wide, short, ill-conditioned, f32) uses
+    the streaming Householder TSQR kernel (nums_qr), which is backward stable for any input."""
     if arr.dim() != 2:
         raise ValueError("qr needs a 2-D block")
     if arr.dtype not in (torch.float64, torch.float32):
@@ -597,10 +679,29 @@ def qr_r(arr):
     if not arr.is_contiguous():
         arr = _materialize(arr)
     m, n = arr.shape
-    r = _empty((min(m, n), n), _lib.numpy_dtype(arr.dtype))
-    LIB.call_ws(LIB.dll.nums_qr, arr.device,
-                ((_lib.dtype_code(arr.dtype), m, n, arr.data_ptr(), n, None, 0, r.data_ptr(), n), (_stream(),)))
-    return r
+    gram_ok = (arr.dtype == torch.float64 and n % 2 == 0 and 2 <= n <= QR_GRAM_MAX_COLS
+               and m >= QR_GRAM_MIN_ASPECT * n and m >= 1024 and arr.data_ptr() % 16 == 0)
+    if not gram_ok:
+        return _householder_r(arr), None
+    low, low_inv, kappa = _gram_factor(arr)
+    if kappa <= QR_GRAM_ACCEPT_KAPPA:
+        QR_STATS["gram"] += 1
+        return _materialize(_transpose_view(low)), kappa
+    if kappa <= QR_GRAM_REFINE_KAPPA:
+        # CholeskyQR2: Q1 = A L^-T, second Gram factor, R = (L1 L2)^T
+        q1 = _empty((m, n), np.float64)
+        gemm_into(q1, arr, False, n, low_inv, True, n, m, n, n)
+        low2, _low2_inv, kappa2 = _gram_factor(q1)
+        if kappa2 <= QR_GRAM_ACCEPT_KAPPA:
+            prod = _empty((n, n), np.float64)
+            gemm_into(prod, low, False, n, low2, False, n, n, n, n)
+            QR_STATS["gram2"] += 1
+            return _materialize(_transpose_view(prod)), kappa
+    return _householder_r(arr), kappa
+
+
+def qr_r(arr):
+    return qr_r_ex(arr)[0]
 
 
 def _inv_nocheck(a):
@@ -612,10 +713,10 @@ def _inv_nocheck(a):
 
 
 def qr_reduced(arr):
-    """(Q, R) with Q (m x k) orthonormal.  R comes from the Householder TSQR kernel; Q is formed as
-    A R^-1 (what the reference itself does one level up, application.py:833-845) followed by one
-    re-orthogonalisation pass (R2 = qr_r(Q); Q <- Q R2^-1; R <- R2 R), which restores
-    orthogonality to working precision for any block whose condition number is below ~1/sqrt(eps).
+    """(Q, R) with Q (m x k) orthonormal.  Q is formed as A R^-1 (what the reference itself does one
+    level up, application.py:833-845); unless R came with a tiny condition bound, one
+    re-orthogonalisation pass (R2 = qr_r(Q); Q <- Q R2^-1; R <- R2 R) restores orthogonality to
+    working precision for any block whose condition number is below ~1/sqrt(eps).
     """
     if arr.dtype not in (torch.float64, torch.float32):
         arr = _materialize(arr, torch.float64)
@@ -623,12 +724,14 @@ def qr_reduced(arr):
         arr = _materialize(arr)
     m, n = arr.shape
     k = min(m, n)
-    r = qr_r(arr)
+    r, kappa = qr_r_ex(arr)
     lead = arr if k == n else _materialize(arr[:, :k])
     r_sq = r if k == n else _materialize(r[:, :k])
     dt = _lib.numpy_dtype(arr.dtype)
     q = _empty((m, k), dt)
     gemm_into(q, lead, False, k, _inv_nocheck(r_sq), False, k, m, k, k)
+    if kappa is not None and kappa <= QR_GRAM_ACCEPT_KAPPA:
+        return q, r
     r2 = qr_r(q)
     q2 = _empty((m, k), dt)
     gemm_into(q2, q, False, k, _inv_nocheck(r2), False, k, m, k, k)

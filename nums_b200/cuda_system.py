@@ -83,9 +83,12 @@ class CudaSystem(object):
 
     def get(self, object_ids):
         object_ids = self.contractions.resolve(object_ids)
-        if isinstance(object_ids, (list, tuple)):
-            return type(object_ids)(self.get(o) for o in object_ids) if isinstance(object_ids, tuple) \
-                else [self.get(o) for o in object_ids]
+        if isinstance(object_ids, list):
+            if all(isinstance(o, torch.Tensor) for o in object_ids):
+                return cuda_compute.download_many(object_ids)
+            return [self.get(o) for o in object_ids]
+        if isinstance(object_ids, tuple):
+            return tuple(self.get(o) for o in object_ids)
         return cuda_compute.download(object_ids)
 
     def remote(self, function, remote_params):

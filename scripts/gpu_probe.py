@@ -50,6 +50,7 @@ def record(name, **kw):
 def main():
     system = CudaSystem()
     system.init()
+    system.contractions.enabled = False   # time the individual kernels, not the deferred chains
     which = set(sys.argv[1:]) or {"copy", "bop", "gemm", "reduce", "lr", "qr", "gemv"}
     props = torch.cuda.get_device_properties(0)
     record("device", gpu=props.name, sms=props.multi_processor_count, mem_gb=props.total_memory / 2 ** 30)

@@ -573,7 +573,8 @@ def test_inv_singular_raises(cuda_system):
 # ----------------------------------------------------------------------------------------------------
 # fused LR kernel vs the reference composition (glms.py:213-240)
 # ----------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("nd", [(1000, 28), (100003, 28), (257, 8), (5000, 30), (4096, 48), (999, 2)])
+@pytest.mark.parametrize("nd", [(1000, 28), (100003, 28), (257, 8), (5000, 30), (4096, 48), (999, 2), (3000, 12),
+                                (70001, 20), (1000, 4), (256, 28), (255, 28), (513, 36)])
 def test_lr_grad_hess(cuda_system, nd):
     from nums_b200 import cuda_compute
     n, d = nd
