@@ -20,6 +20,7 @@ only -- *which per-block kernel calls they issue and in which order*:
 ones the real reference produces (recorded in tests/golden/).  The same code drives either
 ``CudaSystem`` (product) or, in tests and the CPU baseline, an oracle-backed system.
 """
+import functools
 import itertools
 
 import numpy as np
@@ -32,6 +33,7 @@ _UFUNC_ALIASES = {"truediv": "true_divide", "sub": "subtract", "pow": "power", "
                   "ge": "greater_equal", "eq": "equal", "ne": "not_equal"}
 
 
+@functools.lru_cache(maxsize=None)
 def _bop_dtype(op, dt_a, dt_b):
     """array/utils.py:33-42: run the ufunc on two 0-d arrays to learn the output dtype."""
     import scipy.special
@@ -40,10 +42,12 @@ def _bop_dtype(op, dt_a, dt_b):
     return fn(np.array(1, dtype=dt_a), np.array(2, dtype=dt_b)).dtype.type
 
 
+@functools.lru_cache(maxsize=None)
 def _uop_dtype(op, dt):
     return getattr(np, op)(np.array(1, dtype=dt)).dtype.type
 
 
+@functools.lru_cache(maxsize=None)
 def _reduce_dtype(op, dt):
     return getattr(np, op)(np.array([0, 1], dtype=dt)).dtype.type
 

@@ -203,8 +203,12 @@ lr_grad_hess_kernel(const double* __restrict__ X, int64_t ldx, const double* __r
 // issued by a single thread and tracked by an mbarrier -- no per-thread address arithmetic, no
 // LDGSTS issue slots.  With pitch d == 4 or 12 (mod 16) doubles the (row = t, feature = g)
 // fragment reads of the dense tile are bank-conflict free without padding.
+// A ninth warp is the producer (one lane: wait for the slot's `empty` mbarrier, issue the copy);
+// the eight consumer warps free-run through the tiles, each signalling `empty` on its own, so warps
+// drift apart and one warp's scalar pass 1 overlaps the others' tensor-pipe pass 2.
 //   pass 1: lane l owns row l of the warp's 32 rows: z = x . beta with 128-bit shared loads,
-//           mu = sigmoid(z); s = mu (1 - mu) and e = mu - y go to a per-warp shared scratch;
+//           mu = sigmoid(z); s = mu (1 - mu) and e = mu - y go to a per-warp shared scratch
+//           (y is prefetched one tile ahead into a register);
 //   pass 2: 8 rank-4 updates; fragments straight from the tile, s / e broadcast-read from the
 //           scratch (no shuffles); H on the DMMA pipe (upper-triangular 8x8 blocks), g by DFMA.
 // ---------------------------------------------------------------------------------------------
@@ -234,10 +238,15 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
 constexpr int kDenseStages = 3;
+constexpr int kDenseThreads = kLrThreads + 32;   // 8 consumer warps + 1 producer warp
 
 template <int NB>
-__global__ void __launch_bounds__(kLrThreads, 1)
+__global__ void __launch_bounds__(kDenseThreads, 1)
 lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict__ y,
                           const double* __restrict__ beta, int64_t n, int d, double* __restrict__ partial) {
   constexpr int NTRI = NB * (NB + 1) / 2;
@@ -246,33 +255,25 @@ lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict
   double* ring = reinterpret_cast<double*>(lr_smem);                       // kDenseStages tiles
   double* scratch = ring + (size_t)kDenseStages * tile_doubles;            // 8 warps x (32 s + 32 e)
   double* bsm = scratch + 8 * 64;                                          // beta, zero padded to NB*8
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + NB * 8);
+  uint64_t* full = reinterpret_cast<uint64_t*>(bsm + NB * 8);              // data landed (producer -> consumers)
+  uint64_t* empty = full + kDenseStages;                                   // slot released (8 warps -> producer)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  for (int i = threadIdx.x; i < kDenseStages * tile_doubles; i += kLrThreads) ring[i] = 0.0;
-  for (int i = threadIdx.x; i < NB * 8; i += kLrThreads) bsm[i] = i < d ? beta[i] : 0.0;
+  for (int i = threadIdx.x; i < kDenseStages * tile_doubles; i += kDenseThreads) ring[i] = 0.0;
+  for (int i = threadIdx.x; i < NB * 8; i += kDenseThreads) bsm[i] = i < d ? beta[i] : 0.0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kDenseStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kDenseStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   fence_proxy_async();   // the zero fill (generic proxy) happens-before the bulk copies (async proxy)
   __syncthreads();
 
   const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
-  auto issue = [&](int slot, int64_t tile) {   // one thread
-    const int64_t r0 = tile * kTileRows;
-    const int64_t rows = (n - r0 < kTileRows) ? (n - r0) : kTileRows;
-    const uint32_t bytes = (uint32_t)(rows * d * sizeof(double));
-    mbar_expect_tx(&bars[slot], bytes);
-    bulk_copy_g2s(ring + (size_t)slot * tile_doubles, X + r0 * d, bytes, &bars[slot]);
-  };
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kDenseStages - 1; ++s) {
-      const int64_t tl = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-      if (tl < ntiles) issue(s, tl);
-    }
-  }
+  const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   double hacc[NTRI][2];
   double gacc[NB];
@@ -280,72 +281,86 @@ lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict
   for (int i = 0; i < NTRI; ++i) hacc[i][0] = hacc[i][1] = 0.0;
 #pragma unroll
   for (int i = 0; i < NB; ++i) gacc[i] = 0.0;
-  double* my_s = scratch + warp * 64;
-  double* my_e = my_s + 32;
 
-  int slot = 0;
-  uint32_t phase = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    // every warp finished the tile that used the slot we are about to refill
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int64_t nxt = tile + (int64_t)(kDenseStages - 1) * gridDim.x;
-      int nslot = slot + kDenseStages - 1;
-      if (nslot >= kDenseStages) nslot -= kDenseStages;
-      if (nxt < ntiles) {
-        fence_proxy_async();
-        issue(nslot, nxt);
+  if (warp == 8) {
+    // ===== producer warp: one lane feeds the ring with bulk (TMA) copies =====
+    if (lane == 0) {
+      for (int64_t i = 0; i < my_tiles; ++i) {
+        const int slot = (int)(i % kDenseStages);
+        const int64_t round = i / kDenseStages;
+        if (round > 0) mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));
+        fence_proxy_async();   // consumers' generic-proxy reads of this slot precede the async write
+        const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * kTileRows;
+        const int64_t rows = (n - r0 < kTileRows) ? (n - r0) : kTileRows;
+        const uint32_t bytes = (uint32_t)(rows * d * sizeof(double));
+        mbar_expect_tx(&full[slot], bytes);
+        bulk_copy_g2s(ring + (size_t)slot * tile_doubles, X + r0 * d, bytes, &full[slot]);
       }
     }
-    mbar_wait(&bars[slot], phase);
-    const double* xs = ring + (size_t)slot * tile_doubles + (size_t)warp * 32 * d;
-    const int64_t row0 = tile * kTileRows + warp * 32;
+  } else {
+    // ===== consumer warps: 32 rows each per tile, free-running (no CTA barrier per tile) =====
+    double* my_s = scratch + warp * 64;
+    double* my_e = my_s + 32;
+    int64_t myrow = (int64_t)blockIdx.x * kTileRows + warp * 32 + lane;
+    double y_cur = (my_tiles > 0 && myrow < n) ? y[myrow] : 0.0;
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int slot = (int)(i % kDenseStages);
+      mbar_wait(&full[slot], (uint32_t)((i / kDenseStages) & 1));
+      const double* xs = ring + (size_t)slot * tile_doubles + (size_t)warp * 32 * d;
 
-    // pass 1: one row per lane
-    {
-      const double* xr = xs + lane * d;
-      double z0 = 0.0, z1 = 0.0;
-      for (int j = 0; j < d; j += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(xr + j);
-        z0 = fma(v.x, bsm[j], z0);
-        z1 = fma(v.y, bsm[j + 1], z1);
-      }
-      const int64_t myrow = row0 + lane;
-      const bool valid = myrow < n;
-      const double yv = valid ? y[myrow] : 0.0;
-      const double mu = 1.0 / (1.0 + exp(-(z0 + z1)));
-      my_s[lane] = valid ? mu * (1.0 - mu) : 0.0;   // rows past the end may hold stale data: weight 0
-      my_e[lane] = valid ? mu - yv : 0.0;
-    }
-    __syncwarp();
-
-    // pass 2: rank-4 updates
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const double s = my_s[4 * q + t];
-      const double e = my_e[4 * q + t];
-      const double* xr = xs + (4 * q + t) * d + g;
-      double xf[NB], af[NB];
-#pragma unroll
-      for (int bi = 0; bi < NB; ++bi) {
-        xf[bi] = (8 * bi + g < d) ? xr[8 * bi] : 0.0;
-        af[bi] = s * xf[bi];
-        gacc[bi] = fma(e, xf[bi], gacc[bi]);
-      }
-      int idx = 0;
-#pragma unroll
-      for (int bi = 0; bi < NB; ++bi)
-#pragma unroll
-        for (int bj = bi; bj < NB; ++bj) {
-          dmma884(hacc[idx], af[bi], xf[bj]);
-          ++idx;
+      // pass 1: one row per lane
+      {
+        const double* xr = xs + lane * d;
+        double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+        int j = 0;
+        for (; j + 4 <= d; j += 4) {
+          const double2 v = *reinterpret_cast<const double2*>(xr + j);
+          const double2 w = *reinterpret_cast<const double2*>(xr + j + 2);
+          z0 = fma(v.x, bsm[j], z0);
+          z1 = fma(v.y, bsm[j + 1], z1);
+          z2 = fma(w.x, bsm[j + 2], z2);
+          z3 = fma(w.y, bsm[j + 3], z3);
         }
-    }
-    __syncwarp();
-    ++slot;
-    if (slot == kDenseStages) {
-      slot = 0;
-      phase ^= 1u;
+        for (; j < d; j += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(xr + j);
+          z0 = fma(v.x, bsm[j], z0);
+          z1 = fma(v.y, bsm[j + 1], z1);
+        }
+        const bool valid = myrow < n;
+        const double mu = 1.0 / (1.0 + exp(-((z0 + z1) + (z2 + z3))));
+        my_s[lane] = valid ? mu * (1.0 - mu) : 0.0;   // rows past the end may hold stale data: weight 0
+        my_e[lane] = valid ? mu - y_cur : 0.0;
+      }
+      // y of the next tile: issued now, consumed after pass 2 (latency hidden behind the MMAs)
+      myrow += (int64_t)gridDim.x * kTileRows;
+      const double y_next = (i + 1 < my_tiles && myrow < n) ? y[myrow] : 0.0;
+      __syncwarp();
+
+      // pass 2: rank-4 updates
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const double s = my_s[4 * q + t];
+        const double e = my_e[4 * q + t];
+        const double* xr = xs + (4 * q + t) * d + g;
+        double xf[NB], af[NB];
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi) {
+          xf[bi] = (8 * bi + g < d) ? xr[8 * bi] : 0.0;
+          af[bi] = s * xf[bi];
+          gacc[bi] = fma(e, xf[bi], gacc[bi]);
+        }
+        int idx = 0;
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+          for (int bj = bi; bj < NB; ++bj) {
+            dmma884(hacc[idx], af[bi], xf[bj]);
+            ++idx;
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);   // this warp is done with the slot
+      y_cur = y_next;
     }
   }
   __syncthreads();
@@ -354,17 +369,17 @@ lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict
   constexpr int D8 = NB * 8;
   constexpr int PER_WARP = D8 + D8 * D8;
   double* red = ring;
-  for (int i = threadIdx.x; i < 8 * PER_WARP; i += kLrThreads) red[i] = 0.0;
+  for (int i = threadIdx.x; i < 8 * PER_WARP; i += kDenseThreads) red[i] = 0.0;
   __syncthreads();
-  double* mine = red + warp * PER_WARP;
+  if (warp < 8) {
+    double* mine = red + warp * PER_WARP;
 #pragma unroll
-  for (int bi = 0; bi < NB; ++bi) {
-    double v = gacc[bi];
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    if (t == 0) mine[8 * bi + g] = v;
-  }
-  {
+    for (int bi = 0; bi < NB; ++bi) {
+      double v = gacc[bi];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (t == 0) mine[8 * bi + g] = v;
+    }
     int idx = 0;
 #pragma unroll
     for (int bi = 0; bi < NB; ++bi)
@@ -378,7 +393,7 @@ lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict
   }
   __syncthreads();
   double* out = partial + (size_t)blockIdx.x * (d + d * d);
-  for (int i = threadIdx.x; i < d + d * d; i += kLrThreads) {
+  for (int i = threadIdx.x; i < d + d * d; i += kDenseThreads) {
     int src;
     if (i < d) src = i;
     else {
@@ -405,7 +420,7 @@ template <int NB>
 int launch_lr_dense(const double* X, const double* y, const double* beta, int64_t n, int d, double* out,
                     void* ws, size_t ws_bytes, cudaStream_t s) {
   const size_t tile_bytes = (size_t)kTileRows * d * sizeof(double);
-  const size_t smem = kDenseStages * tile_bytes + (8 * 64 + NB * 8) * sizeof(double) + kDenseStages * sizeof(uint64_t);
+  const size_t smem = kDenseStages * tile_bytes + (8 * 64 + NB * 8) * sizeof(double) + 2 * kDenseStages * sizeof(uint64_t);
   const int len = d + d * d;
   const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
   int grid = sm_count();
@@ -413,7 +428,7 @@ int launch_lr_dense(const double* X, const double* y, const double* beta, int64_
   if (grid < 1) grid = 1;
   NUMS_NEED_WS((size_t)grid * len * sizeof(double), ws_bytes);
   NUMS_CUDA_OK(cudaFuncSetAttribute(lr_grad_hess_dense_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lr_grad_hess_dense_kernel<NB><<<grid, kLrThreads, smem, s>>>(X, y, beta, n, d, static_cast<double*>(ws));
+  lr_grad_hess_dense_kernel<NB><<<grid, kDenseThreads, smem, s>>>(X, y, beta, n, d, static_cast<double*>(ws));
   NUMS_LAUNCH_OK();
   lr_fold_kernel<<<(len + 255) / 256, 256, 0, s>>>(static_cast<const double*>(ws), grid, len, out);
   NUMS_LAUNCH_OK();

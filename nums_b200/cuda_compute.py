@@ -118,6 +118,9 @@ def _to_pinned(t):
 
 def download(t):
     """Device tensor -> numpy array (synchronises the current stream)."""
+    if isinstance(t, Touched):
+        torch.cuda.current_stream().synchronize()
+        return t.ok
     if not isinstance(t, torch.Tensor):
         return t
     if t.numel() * t.element_size() < (1 << 16):
@@ -175,6 +178,33 @@ def _operand(a, shape, transposed):
     return a
 
 
+def _broadcast_shape(s1, s2):
+    """NumPy broadcasting of two shapes (pure Python: this sits on the per-block dispatch path)."""
+    if s1 == s2:
+        return s1
+    n1, n2 = len(s1), len(s2)
+    out = []
+    for i in range(max(n1, n2)):
+        d1 = s1[n1 - 1 - i] if i < n1 else 1
+        d2 = s2[n2 - 1 - i] if i < n2 else 1
+        if d1 != d2 and d1 != 1 and d2 != 1:
+            raise ValueError("operands could not be broadcast together with shapes %s %s" % (s1, s2))
+        out.append(d2 if d1 == 1 else d1)
+    return tuple(reversed(out))
+
+
+_REDUCE_TYPES = {}
+
+
+def reduce_type(op_name, dt):
+    key = (op_name, dt)
+    hit = _REDUCE_TYPES.get(key)
+    if hit is None:
+        hit = getattr(np, op_name)(np.zeros((1,), dtype=dt)).dtype
+        _REDUCE_TYPES[key] = hit
+    return hit
+
+
 def _np_dtype(name):
     if isinstance(name, str):
         return np.dtype({"int": np.int64, "float": np.float64, "bool": np.bool_}.get(name) or getattr(np, name))
@@ -226,12 +256,21 @@ def _apply_sel(t, sel):
     return t[sel]
 
 
+class Touched(object):
+    """Result of ``touch``: resolves to a bool once the stream has been synchronised (by ``get``)."""
+    __slots__ = ("ok",)
+
+    def __init__(self, ok):
+        self.ok = ok
+
+
 class ComputeCls(_ComputeImp):
     # ------------------------------------------------------------------ I/O-ish
     def touch(self, arr):
-        """Synchronisation point (numpy_compute.py:88-89)."""
-        torch.cuda.current_stream().synchronize()
-        return isinstance(arr, torch.Tensor)
+        """"Touch" a block (numpy_compute.py:88-89).  Returns a token; waiting happens when the token
+        is fetched with ``system.get`` -- BlockArray.touch collects one token per block and gets them
+        all at once (blockarray.py:117-126), which costs one stream synchronisation, not one per block."""
+        return Touched(isinstance(arr, torch.Tensor))
 
     def empty(self, grid_entry, grid_meta):
         grid = ArrayGrid.from_meta(grid_meta)
@@ -370,25 +409,14 @@ class ComputeCls(_ComputeImp):
         return out
 
     def xlogy(self, arr_x, arr_y):
-        return self._elementwise("xlogy", upload(arr_x), upload(arr_y))
-
-    def _elementwise(self, name, a1, a2):
-        if name not in _lib.BOP_CODE:
-            raise NotImplementedError("binary ufunc %s" % name)
-        loop, out_dt = bop_types(name, _lib.numpy_dtype(a1.dtype), _lib.numpy_dtype(a2.dtype))
-        shape = torch.broadcast_shapes(tuple(a1.shape), tuple(a2.shape))
-        out = _empty(shape, out_dt)
-        if out.numel():
-            LIB.check(LIB.dll.nums_bop(_lib.BOP_CODE[name], _lib.dtype_code(loop), describe(a1), describe(a2),
-                                       describe(out), _stream()))
-        return out
+        return elementwise("xlogy", upload(arr_x), upload(arr_y))
 
     def bop(self, op, a1, a2, a1_shape, a2_shape, a1_T, a2_T, axes):
         a1 = _operand(a1, a1_shape, a1_T)
         a2 = _operand(a2, a2_shape, a2_T)
         if op == "tensordot":
             return tensordot(a1, a2, axes)
-        return self._elementwise(_SHORT_OP_NAMES.get(op, op), a1, a2)
+        return elementwise(_SHORT_OP_NAMES.get(op, op), a1, a2)
 
     # ------------------------------------------------------------------ reductions
     def reduce_axis(self, op_name, arr, axis, keepdims, transposed):
@@ -407,7 +435,7 @@ class ComputeCls(_ComputeImp):
         if not arr.is_contiguous():
             arr = _materialize(arr)
         in_dt = _lib.numpy_dtype(arr.dtype)
-        out_dt = getattr(np, op_name)(np.zeros((1,), dtype=in_dt)).dtype
+        out_dt = reduce_type(op_name, in_dt)
         shape = tuple(arr.shape)
         if axis is None:
             outer, red, inner = 1, int(np.prod(shape, dtype=np.int64)), 1
@@ -501,7 +529,7 @@ class ComputeCls(_ComputeImp):
         a, b = upload(a), upload(b)
         dt = np.result_type(_lib.numpy_dtype(a.dtype), _lib.numpy_dtype(b.dtype))
         tdt = _lib.torch_dtype(dt)
-        shape = torch.broadcast_shapes(tuple(a.shape), tuple(b.shape))
+        shape = _broadcast_shape(tuple(a.shape), tuple(b.shape))
         a = _materialize(a.expand(shape), tdt) if (a.dtype != tdt or tuple(a.shape) != tuple(shape) or not a.is_contiguous()) else a
         b = _materialize(b.expand(shape), tdt) if (b.dtype != tdt or tuple(b.shape) != tuple(shape) or not b.is_contiguous()) else b
         flag = _empty((), np.bool_)
@@ -545,8 +573,22 @@ class ComputeCls(_ComputeImp):
 
 
 # ---------------------------------------------------------------------------------------------
-# contraction / factorisation helpers (module level so workloads can reuse them)
+# helpers (module level: ComputeCls itself must expose nothing but the 28 interface methods,
+# the reference's SerialSystem.init looks every method up in ComputeInterface, systems.py:76-89)
 # ---------------------------------------------------------------------------------------------
+def elementwise(name, a1, a2):
+    """np.<name>(a1, a2) with NumPy type resolution and broadcasting (nums_bop)."""
+    if name not in _lib.BOP_CODE:
+        raise NotImplementedError("binary ufunc %s" % name)
+    loop, out_dt = bop_types(name, _lib.numpy_dtype(a1.dtype), _lib.numpy_dtype(a2.dtype))
+    shape = _broadcast_shape(tuple(a1.shape), tuple(a2.shape))
+    out = _empty(shape, out_dt)
+    if out.numel():
+        LIB.check(LIB.dll.nums_bop(_lib.BOP_CODE[name], _lib.dtype_code(loop), describe(a1), describe(a2),
+                                   describe(out), _stream()))
+    return out
+
+
 def _as_matrix(t, rows, cols):
     """View a tensor as a (rows, cols) matrix stored row-major or column-major without copying
     when possible.  Returns (tensor, transposed_flag, pitch)."""
@@ -632,22 +674,31 @@ def _householder_r(arr):
     return r
 
 
-def _fro2(t):
-    """sum(t * t) as a 0-d device tensor (two tiny launches)."""
-    n = t.numel()
-    sq = _empty((n,), np.float64)
-    flat = t.view(n)
-    LIB.check(LIB.dll.nums_bop(_lib.BOP_CODE["multiply"], _lib.F64, describe(flat), describe(flat), describe(sq), _stream()))
-    out = _empty((), np.float64)
-    LIB.call_ws(LIB.dll.nums_reduce, t.device,
-                ((_lib.REDUCE_CODE["sum"], sq.data_ptr(), _lib.F64, 1, n, 1, out.data_ptr(), _lib.F64), (_stream(),)))
+def _norm_1_inf(t):
+    """(max column abs-sum, max row abs-sum) of a square matrix, as two 0-d device tensors."""
+    n = t.shape[0]
+    absolute = _empty((n, n), np.float64)
+    LIB.check(LIB.dll.nums_uop(_lib.UOP_CODE["absolute"], _lib.F64, describe(t), describe(absolute), _stream()))
+    out = []
+    for outer, red, inner in ((1, n, n), (n, n, 1)):      # axis 0 sums (columns), axis 1 sums (rows)
+        sums = _empty((n,), np.float64)
+        LIB.call_ws(LIB.dll.nums_reduce, t.device,
+                    ((_lib.REDUCE_CODE["sum"], absolute.data_ptr(), _lib.F64, outer, red, inner, sums.data_ptr(),
+                      _lib.F64), (_stream(),)))
+        top = _empty((), np.float64)
+        LIB.call_ws(LIB.dll.nums_reduce, t.device,
+                    ((_lib.REDUCE_CODE["max"], sums.data_ptr(), _lib.F64, 1, n, 1, top.data_ptr(), _lib.F64),
+                     (_stream(),)))
+        out.append(top)
     return out
 
 
 def _gram_factor(a):
     """Cholesky factor L (lower) of a^T a, its inverse, and a rigorous bound on cond_2(a):
-    cond(a) = cond(L) <= ||L||_F ||L^-1||_F.  Returns (L, Linv, kappa_bound); kappa_bound is inf if
-    the Gram matrix is not numerically positive definite.  One 20-byte read-back."""
+    cond_2(a) = cond_2(L) <= sqrt(|L|_1 |L|_inf |L^-1|_1 |L^-1|_inf)   (|M|_2^2 <= |M|_1 |M|_inf),
+    which is tight for the nearly diagonal factors of well-conditioned blocks (a Frobenius bound
+    would be off by a factor n).  Returns (L, Linv, kappa_bound); the bound is inf if the Gram matrix
+    is not numerically positive definite.  One 40-byte read-back."""
     m, n = a.shape
     gram = _empty((n, n), np.float64)
     gemm_into(gram, a, True, n, a, False, n, n, n, m)
@@ -656,14 +707,15 @@ def _gram_factor(a):
     LIB.call_ws(LIB.dll.nums_cholesky, a.device,
                 ((_lib.F64, n, gram.data_ptr(), n, low.data_ptr(), n, info.data_ptr()), (_stream(),)))
     low_inv = _inv_nocheck(low)
-    stats = _empty((3,), np.float64)
+    stats = _empty((5,), np.float64)
     _copy_into(stats[0], info)
-    _copy_into(stats[1], _fro2(low))
-    _copy_into(stats[2], _fro2(low_inv))
-    failed, n_l, n_li = (float(v) for v in stats.cpu())   # 24-byte D2H, the one sync of this path
-    if failed != 0 or not np.isfinite(n_l * n_li):
+    for i, v in enumerate(_norm_1_inf(low) + _norm_1_inf(low_inv)):
+        _copy_into(stats[1 + i], v)
+    failed, l1, linf, i1, iinf = (float(v) for v in stats.cpu())   # 40-byte D2H, the one sync of this path
+    bound = l1 * linf * i1 * iinf
+    if failed != 0 or not np.isfinite(bound):
         return low, low_inv, float("inf")
-    return low, low_inv, float(np.sqrt(n_l * n_li))
+    return low, low_inv, float(np.sqrt(bound))
 
 
 def qr_r_ex(arr):

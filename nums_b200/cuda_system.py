@@ -86,6 +86,9 @@ class CudaSystem(object):
         if isinstance(object_ids, list):
             if all(isinstance(o, torch.Tensor) for o in object_ids):
                 return cuda_compute.download_many(object_ids)
+            if object_ids and all(isinstance(o, cuda_compute.Touched) for o in object_ids):
+                torch.cuda.current_stream().synchronize()     # one wait for a whole BlockArray.touch()
+                return [o.ok for o in object_ids]
             return [self.get(o) for o in object_ids]
         if isinstance(object_ids, tuple):
             return tuple(self.get(o) for o in object_ids)
@@ -112,11 +115,14 @@ class CudaSystem(object):
         kwargs.pop("syskwargs", None)
         q = self.contractions
         if name == "bop" and q.enabled:
-            lazy = self._try_defer(args, kwargs)
-            if lazy is not None:
-                return lazy
-        args = tuple(q.resolve(a) for a in args)
-        kwargs = {k: q.resolve(v) for k, v in kwargs.items()}
+            op = args[0] if args else kwargs.get("op")
+            if op == "tensordot" or (op == "add" and q._pending):
+                lazy = self._try_defer(args, kwargs)
+                if lazy is not None:
+                    return lazy
+        if q._pending or q.materialized_seen:
+            args = tuple(q.resolve(a) for a in args)
+            kwargs = {k: q.resolve(v) for k, v in kwargs.items()}
         return self.remote_functions[name](*args, **kwargs)
 
     def _try_defer(self, args, kwargs):

@@ -51,6 +51,7 @@ class ContractionQueue(object):
         self._pending = []   # weak references to unmaterialised contractions, in creation order
         self.flushes = 0
         self.enabled = True
+        self.materialized_seen = False   # deferred handles exist somewhere: keep resolving arguments
 
     # -- building -------------------------------------------------------------------------------
     def tensordot(self, a1, a2, a1_shape, a2_shape, a1_T, a2_T, axes):
@@ -94,6 +95,7 @@ class ContractionQueue(object):
 
     def _register(self, d):
         self._pending.append(weakref.ref(d))
+        self.materialized_seen = True
         return d
 
     # -- materialising ----------------------------------------------------------------------------

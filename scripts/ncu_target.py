@@ -15,8 +15,19 @@ if which == "gemm":
     B = torch.randn((n, n), dtype=torch.float64, device=dev)
     for _ in range(4):
         C = system.bop("tensordot", A, B, (n, n), (n, n), False, False, axes=1, syskwargs={})
+elif which == "grouped":
+    from nums_b200 import blocks
+    n, bs = 8192, 2048
+    app = blocks.ArrayApp(system)
+    A = blocks.BlockArray(blocks.ArrayGrid((n, n), (bs, bs), "float64"), system)
+    B = blocks.BlockArray(blocks.ArrayGrid((n, n), (bs, bs), "float64"), system)
+    for e in A.grid.get_entry_iterator():
+        A.blocks[e].oid = torch.randn((bs, bs), dtype=torch.float64, device=dev)
+        B.blocks[e].oid = torch.randn((bs, bs), dtype=torch.float64, device=dev)
+    for _ in range(3):
+        (A @ B).touch()
 elif which == "bop":
-    n = 100_000_000
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000_000
     u = torch.rand(n, dtype=torch.float64, device=dev); v = torch.rand(n, dtype=torch.float64, device=dev)
     for _ in range(4):
         w = system.bop("add", u, v, (n,), (n,), False, False, axes=None, syskwargs={})
