@@ -329,6 +329,100 @@ cholesky_kernel(const T* __restrict__ A, int64_t lda, int n, T* __restrict__ out
   if (tid == 0 && info != nullptr) *info = failed;
 }
 
+
+// =====================================================================================
+// SVD of a square matrix: one-sided Jacobi (Hestenes), one CTA
+// =====================================================================================
+// Works on At (row j = column j of A) and Vt (row j = column j of V) in global scratch (L2
+// resident for the n <= 1024 this path sees: svd is only ever applied to the n x n R factor,
+// application.py:946).  Each round of the round-robin ordering rotates n/2 disjoint column
+// pairs, one warp per pair; sweeps repeat until no pair needed a rotation.
+template <typename T>
+__global__ void __launch_bounds__(kLaThreads, 1)
+svd_jacobi_kernel(const T* __restrict__ A, int64_t lda, int n, T* __restrict__ U, T* __restrict__ S,
+                  T* __restrict__ Vt_out, T* __restrict__ At, T* __restrict__ Vt, T* __restrict__ sig) {
+  __shared__ int rotated;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kLaThreads / 32;
+  for (int e = tid; e < n * n; e += kLaThreads) {
+    const int j = e / n, i = e - j * n;   // At[j][i] = A[i][j]
+    At[e] = A[(int64_t)i * lda + j];
+    Vt[e] = (i == j) ? T(1) : T(0);
+  }
+  __syncthreads();
+  const int np = n + (n & 1);             // pad to even with a dummy column
+  const T eps = std::is_same<T, double>::value ? T(1.1e-16) : T(6e-8);
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+    for (int round = 0; round < np - 1; ++round) {
+      for (int k = warp; k < np / 2; k += kWarps) {
+        int p, q;
+        if (k == 0) { p = np - 1; q = round; }
+        else { p = (round + k) % (np - 1); q = (round - k + np - 1) % (np - 1); }
+        if (p >= n || q >= n) continue;   // dummy column
+        if (p > q) { const int tmp = p; p = q; q = tmp; }
+        T* ap = At + (size_t)p * n;
+        T* aq = At + (size_t)q * n;
+        T alpha = T(0), beta = T(0), gamma = T(0);
+        for (int i = lane; i < n; i += 32) {
+          const T x = ap[i], y = aq[i];
+          alpha += x * x; beta += y * y; gamma += x * y;
+        }
+        alpha = warp_sum(alpha); beta = warp_sum(beta); gamma = warp_sum(gamma);
+        if (fabs(gamma) > eps * sqrt(alpha * beta) && alpha > T(0) && beta > T(0)) {
+          const T zeta = (beta - alpha) / (T(2) * gamma);
+          const T tt = (zeta >= T(0) ? T(1) : T(-1)) / (fabs(zeta) + sqrt(T(1) + zeta * zeta));
+          const T c = T(1) / sqrt(T(1) + tt * tt), sn = c * tt;
+          T* vp = Vt + (size_t)p * n;
+          T* vq = Vt + (size_t)q * n;
+          for (int i = lane; i < n; i += 32) {
+            const T x = ap[i], y = aq[i];
+            ap[i] = c * x - sn * y;
+            aq[i] = sn * x + c * y;
+            const T vx = vp[i], vy = vq[i];
+            vp[i] = c * vx - sn * vy;
+            vq[i] = sn * vx + c * vy;
+          }
+          if (lane == 0) rotated = 1;
+        }
+      }
+      __syncthreads();
+    }
+    const int again = rotated;
+    __syncthreads();
+    if (!again) break;
+  }
+  // singular values, descending order
+  for (int j = warp; j < n; j += kWarps) {
+    T acc = T(0);
+    for (int i = lane; i < n; i += 32) { const T x = At[(size_t)j * n + i]; acc += x * x; }
+    acc = warp_sum(acc);
+    if (lane == 0) sig[j] = sqrt(acc);
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += kLaThreads) {
+    const T sj = sig[j];
+    int rank = 0;
+    for (int i = 0; i < n; ++i) {
+      const T si = sig[i];
+      if (si > sj || (si == sj && i < j)) ++rank;
+    }
+    S[rank] = sj;
+    // stash the destination in the (now unused) diagonal-free slot: reuse sig as int via a second pass
+    reinterpret_cast<int*>(sig + n)[j] = rank;
+  }
+  __syncthreads();
+  const int* rank_of = reinterpret_cast<const int*>(sig + n);
+  for (int e = tid; e < n * n; e += kLaThreads) {
+    const int j = e / n, i = e - j * n;
+    const int r = rank_of[j];
+    const T sj = sig[j];
+    U[(size_t)i * n + r] = sj > T(0) ? At[e] / sj : T(0);
+    Vt_out[(size_t)r * n + i] = Vt[e];
+  }
+}
+
 template <typename T, typename K>
 int run_single_cta(K kernel, int64_t n, const T* A, int64_t lda, T* out, int64_t ldo, int32_t* info, void* ws,
                    size_t ws_bytes, cudaStream_t s, const char* what) {
@@ -338,6 +432,19 @@ int run_single_cta(K kernel, int64_t n, const T* A, int64_t lda, T* out, int64_t
   if (!use_smem) NUMS_NEED_WS((size_t)n * n * sizeof(T), ws_bytes);
   if (use_smem) NUMS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel<<<1, kLaThreads, use_smem ? smem : 0, s>>>(A, lda, (int)n, out, ldo, static_cast<T*>(ws), use_smem ? 1 : 0, info);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
+template <typename T>
+int run_svd(int64_t n, const T* A, int64_t lda, T* U, T* S, T* Vt, void* ws, size_t ws_bytes, cudaStream_t s) {
+  NUMS_REQUIRE(n >= 1 && n <= 1024, "svd: n = %lld outside the supported range [1, 1024]", (long long)n);
+  const size_t need = ((size_t)2 * n * n + 3 * n + 8) * sizeof(T);
+  NUMS_NEED_WS(need, ws_bytes);
+  T* At = static_cast<T*>(ws);
+  T* Vw = At + (size_t)n * n;
+  T* sig = Vw + (size_t)n * n;   // n singular values followed by n ints (rank table)
+  svd_jacobi_kernel<T><<<1, kLaThreads, 0, s>>>(A, lda, (int)n, U, S, Vt, At, Vw, sig);
   NUMS_LAUNCH_OK();
   return NUMS_OK;
 }
@@ -386,6 +493,13 @@ extern "C" int nums_cholesky(int dtype, int64_t n, const void* A, int64_t lda, v
 extern "C" int nums_svd(int dtype, int64_t n, const void* A, int64_t lda, void* U, void* S, void* Vt,
                         void* ws, size_t ws_bytes, void* stream) {
   using namespace nums;
-  (void)dtype; (void)n; (void)A; (void)lda; (void)U; (void)S; (void)Vt; (void)ws; (void)ws_bytes; (void)stream;
-  NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "svd: not implemented yet in this build");
+  NUMS_REQUIRE(A && U && S && Vt, "svd: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == NUMS_F64)
+    return run_svd<double>(n, static_cast<const double*>(A), lda, static_cast<double*>(U), static_cast<double*>(S),
+                           static_cast<double*>(Vt), ws, ws_bytes, s);
+  if (dtype == NUMS_F32)
+    return run_svd<float>(n, static_cast<const float*>(A), lda, static_cast<float*>(U), static_cast<float*>(S),
+                          static_cast<float*>(Vt), ws, ws_bytes, s);
+  NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "svd: dtype %s", dtype_name(dtype));
 }
