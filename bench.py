@@ -405,6 +405,24 @@ def run_gpu(args):
     e2e_value = FLOPS_PER_STEP * e2e_steps / float(e2e_seconds.item()) / 1e12
     bytes_matrix = 8 * N_MATMUL * N_MATMUL
 
+    # ---- parity spot check of this run's output (rank 0): one C block against NumPy on the host ------
+    verified = None
+    if rank == 0:
+        if world == 1:
+            c_dev = system.get((A @ B).blocks[0, 0].oid)
+        else:
+            c_all = summa.run(mine_a, mine_b)
+            key = sorted(c_all)[0]
+            c_dev = system.get(c_all[key])
+        i, j = (0, 0) if world == 1 else key
+        ref = np.zeros((BLOCK, BLOCK))
+        for k in range(GRID):
+            ref += a_host[(i, k)] @ b_host[(k, j)]
+        verified = float(np.linalg.norm(c_dev - ref) / np.linalg.norm(ref))
+    elif world > 1:
+        summa.run(mine_a, mine_b)      # collective: every rank takes part in the verification pass
+    sync_all()
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -474,6 +492,8 @@ def run_gpu(args):
                 "h2d_bytes_per_step": 2 * bytes_matrix, "d2h_bytes_per_step": bytes_matrix, "steps": e2e_steps,
                 "what": "pinned host blocks -> system.put -> A @ B through the block kernel interface -> C.get() on the host"},
         "gpu_launches": int(launches),
+        "parity_check": {"what": "one 2048x2048 block of C vs NumPy on the host (relative Frobenius error)",
+                         "rel_err": verified, "bar": 1e-10},
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

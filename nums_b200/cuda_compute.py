@@ -568,8 +568,22 @@ class ComputeCls(_ComputeImp):
         return _single_cta_factor(LIB.dll.nums_inv, upload(arr), "Singular matrix")
 
     def svd(self, arr):
+        """u, sigma, vT of a square block (numpy_compute.py:251-254; only ever the n x n R factor,
+        application.py:946).  One-sided Jacobi; singular vectors are unique up to signs only."""
         arr = upload(arr)
-        raise NotImplementedError("svd is not implemented by libnumscuda yet")
+        if arr.dim() != 2 or arr.shape[0] != arr.shape[1]:
+            raise NotImplementedError("svd of non-square blocks is not on the hot path")
+        if arr.dtype not in (torch.float64, torch.float32):
+            arr = _materialize(arr, torch.float64)
+        if not arr.is_contiguous():
+            arr = _materialize(arr)
+        n = arr.shape[0]
+        dt = _lib.numpy_dtype(arr.dtype)
+        u, sigma, vt = _empty((n, n), dt), _empty((n,), dt), _empty((n, n), dt)
+        LIB.call_ws(LIB.dll.nums_svd, arr.device,
+                    ((_lib.dtype_code(arr.dtype), n, arr.data_ptr(), n, u.data_ptr(), sigma.data_ptr(), vt.data_ptr()),
+                     (_stream(),)))
+        return u, sigma, vt
 
 
 # ---------------------------------------------------------------------------------------------

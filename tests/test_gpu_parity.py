@@ -627,3 +627,18 @@ def test_deferred_blocked_matmul(cuda_system, shapes):
     c = (a @ b) + (a @ b)
     d = c * 2.0
     assert rel_fro(d.get(), 4.0 * want) <= GEMM_TOL
+
+
+@pytest.mark.parametrize("n", [1, 2, 9, 28, 64, 128, 129])
+def test_svd(cuda_system, oracle, n):
+    rng = np.random.default_rng(64)
+    for make in (lambda: rng.standard_normal((n, n)), lambda: np.triu(rng.standard_normal((n, n)))):
+        A = make()
+        u, s, vt = (cuda_system.get(x) for x in cuda_system.svd(cuda_system.put(A), syskwargs={}))
+        uw, sw, vtw = oracle.svd(A)
+        assert u.shape == uw.shape and s.shape == sw.shape and vt.shape == vtw.shape
+        assert np.all(np.diff(s) <= 0)
+        assert np.abs(s - sw).max() <= 1e-10 * sw[0]
+        assert rel_fro((u * s) @ vt, A) <= 1e-10
+        assert np.linalg.norm(u.T @ u - np.eye(n)) <= 1e-10 * n
+        assert np.linalg.norm(vt @ vt.T - np.eye(n)) <= 1e-10 * n
