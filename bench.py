@@ -151,6 +151,15 @@ def cpu_matmul_sample(c_blocks, a_host, b_host):
     return time.perf_counter() - t0, done
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=len(os.sched_getaffinity(0)), user_api="blas")
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def cpu_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -164,6 +173,7 @@ def cpu_threads():
 
 def measure_cpu(a_host, b_host, target_seconds=12.0):
     """Bounded sample of the CPU path: as many C blocks as fit in about `target_seconds`."""
+    use_all_host_threads()
     probe, _ = cpu_matmul_sample(1, a_host, b_host)
     blocks = int(max(1, min(GRID * GRID, target_seconds // max(probe, 1e-3))))
     seconds, done = cpu_matmul_sample(blocks, a_host, b_host) if blocks > 1 else (probe, 1)
@@ -178,6 +188,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     a_host, b_host = matmul_blocks_host(pinned=False)
     probe, _ = cpu_matmul_sample(1, a_host, b_host)
     per_step_blocks = int(max(1, min(GRID * GRID, 20.0 // max(probe, 1e-3) // max(args.steps + args.warmup, 1))))
@@ -283,7 +294,7 @@ def other_workloads(system, quick):
     iters_fused = 10
 
     def fused():
-        multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters_fused, cc.lr_grad_hess)
+        multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters_fused, cc.lr_grad_hess_blocks)
     t = timed(fused, 2 if quick else 3)
     out["newton_lr_fused"] = {
         "value": t / iters_fused, "unit": "s/iter",

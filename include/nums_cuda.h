@@ -226,6 +226,14 @@ int nums_svd(int dtype, int64_t n, const void* A, int64_t lda, void* U, void* S,
 int nums_lr_grad_hess(int64_t n, int64_t d, const double* X, int64_t ldx, const double* y,
                       const double* beta, double* out, void* ws, size_t ws_bytes, void* stream);
 
+/* Same, for up to 16 dense row blocks (ldx == d) of one row-sharded matrix in a single launch: the G
+ * row blocks of X / y that glms.newton walks (glms.py:362-372).  X_host / y_host / rows_host are
+ * HOST arrays of device pointers / row counts.  Needs d == 4 or 12 (mod 16), d <= 48 (the shapes
+ * served by the bulk-copy kernel, e.g. HIGGS d = 28); otherwise NUMS_ERR_UNSUPPORTED. */
+int nums_lr_grad_hess_blocks(int nblocks, const double* const* X_host, const double* const* y_host,
+                             const int64_t* rows_host, int64_t d, const double* beta, double* out,
+                             void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

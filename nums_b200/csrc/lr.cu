@@ -244,11 +244,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 constexpr int kDenseStages = 3;
 constexpr int kDenseThreads = kLrThreads + 32;   // 8 consumer warps + 1 producer warp
+constexpr int kMaxLrBlocks = 16;
+
+// Several row blocks of one row-sharded matrix handled by a single launch (the G row blocks of
+// X / y in glms.newton): tile t belongs to block b with tile_begin[b] <= t < tile_begin[b + 1].
+struct LrBlocks {
+  const double* X[kMaxLrBlocks];
+  const double* y[kMaxLrBlocks];
+  int64_t rows[kMaxLrBlocks];
+  int64_t tile_begin[kMaxLrBlocks + 1];
+  int count;
+};
+
+__device__ __forceinline__ int lr_find_block(const LrBlocks& blk, int64_t tile) {
+  int b = 0;
+  while (b + 1 < blk.count && tile >= blk.tile_begin[b + 1]) ++b;
+  return b;
+}
 
 template <int NB>
 __global__ void __launch_bounds__(kDenseThreads, 1)
-lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict__ y,
-                          const double* __restrict__ beta, int64_t n, int d, double* __restrict__ partial) {
+lr_grad_hess_dense_kernel(const __grid_constant__ LrBlocks blk, const double* __restrict__ beta, int d,
+                          double* __restrict__ partial) {
   constexpr int NTRI = NB * (NB + 1) / 2;
   extern __shared__ __align__(128) unsigned char lr_smem[];
   const int tile_doubles = kTileRows * d;
@@ -272,7 +289,7 @@ lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict
   fence_proxy_async();   // the zero fill (generic proxy) happens-before the bulk copies (async proxy)
   __syncthreads();
 
-  const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
+  const int64_t ntiles = blk.tile_begin[blk.count];
   const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   double hacc[NTRI][2];
@@ -290,19 +307,28 @@ lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict
         const int64_t round = i / kDenseStages;
         if (round > 0) mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));
         fence_proxy_async();   // consumers' generic-proxy reads of this slot precede the async write
-        const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * kTileRows;
-        const int64_t rows = (n - r0 < kTileRows) ? (n - r0) : kTileRows;
+        const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
+        const int b = lr_find_block(blk, tile);
+        const int64_t r0 = (tile - blk.tile_begin[b]) * kTileRows;
+        const int64_t rows = (blk.rows[b] - r0 < kTileRows) ? (blk.rows[b] - r0) : kTileRows;
         const uint32_t bytes = (uint32_t)(rows * d * sizeof(double));
         mbar_expect_tx(&full[slot], bytes);
-        bulk_copy_g2s(ring + (size_t)slot * tile_doubles, X + r0 * d, bytes, &full[slot]);
+        bulk_copy_g2s(ring + (size_t)slot * tile_doubles, blk.X[b] + r0 * d, bytes, &full[slot]);
       }
     }
   } else {
     // ===== consumer warps: 32 rows each per tile, free-running (no CTA barrier per tile) =====
     double* my_s = scratch + warp * 64;
     double* my_e = my_s + 32;
-    int64_t myrow = (int64_t)blockIdx.x * kTileRows + warp * 32 + lane;
-    double y_cur = (my_tiles > 0 && myrow < n) ? y[myrow] : 0.0;
+    // (y value, validity) of this lane's row in a given tile
+    auto fetch_y = [&](int64_t tile, bool& valid) -> double {
+      const int b = lr_find_block(blk, tile);
+      const int64_t row = (tile - blk.tile_begin[b]) * kTileRows + warp * 32 + lane;
+      valid = row < blk.rows[b];
+      return valid ? blk.y[b][row] : 0.0;
+    };
+    bool valid_cur = false;
+    double y_cur = my_tiles > 0 ? fetch_y(blockIdx.x, valid_cur) : 0.0;
     for (int64_t i = 0; i < my_tiles; ++i) {
       const int slot = (int)(i % kDenseStages);
       mbar_wait(&full[slot], (uint32_t)((i / kDenseStages) & 1));
@@ -326,14 +352,14 @@ lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict
           z0 = fma(v.x, bsm[j], z0);
           z1 = fma(v.y, bsm[j + 1], z1);
         }
-        const bool valid = myrow < n;
+        const bool valid = valid_cur;
         const double mu = 1.0 / (1.0 + exp(-((z0 + z1) + (z2 + z3))));
         my_s[lane] = valid ? mu * (1.0 - mu) : 0.0;   // rows past the end may hold stale data: weight 0
         my_e[lane] = valid ? mu - y_cur : 0.0;
       }
       // y of the next tile: issued now, consumed after pass 2 (latency hidden behind the MMAs)
-      myrow += (int64_t)gridDim.x * kTileRows;
-      const double y_next = (i + 1 < my_tiles && myrow < n) ? y[myrow] : 0.0;
+      bool valid_next = false;
+      const double y_next = (i + 1 < my_tiles) ? fetch_y((int64_t)blockIdx.x + (i + 1) * gridDim.x, valid_next) : 0.0;
       __syncwarp();
 
       // pass 2: rank-4 updates
@@ -361,6 +387,7 @@ lr_grad_hess_dense_kernel(const double* __restrict__ X, const double* __restrict
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[slot]);   // this warp is done with the slot
       y_cur = y_next;
+      valid_cur = valid_next;
     }
   }
   __syncthreads();
@@ -417,37 +444,59 @@ lr_fold_kernel(const double* __restrict__ partial, int parts, int len, double* _
 }
 
 template <int NB>
-int launch_lr_dense(const double* X, const double* y, const double* beta, int64_t n, int d, double* out,
-                    void* ws, size_t ws_bytes, cudaStream_t s) {
+int launch_lr_dense(const LrBlocks& blk, const double* beta, int d, double* out, void* ws, size_t ws_bytes,
+                    cudaStream_t s) {
   const size_t tile_bytes = (size_t)kTileRows * d * sizeof(double);
   const size_t smem = kDenseStages * tile_bytes + (8 * 64 + NB * 8) * sizeof(double) + 2 * kDenseStages * sizeof(uint64_t);
   const int len = d + d * d;
-  const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
+  const int64_t ntiles = blk.tile_begin[blk.count];
   int grid = sm_count();
   if (grid > ntiles) grid = (int)ntiles;
   if (grid < 1) grid = 1;
   NUMS_NEED_WS((size_t)grid * len * sizeof(double), ws_bytes);
   NUMS_CUDA_OK(cudaFuncSetAttribute(lr_grad_hess_dense_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lr_grad_hess_dense_kernel<NB><<<grid, kDenseThreads, smem, s>>>(X, y, beta, n, d, static_cast<double*>(ws));
+  lr_grad_hess_dense_kernel<NB><<<grid, kDenseThreads, smem, s>>>(blk, beta, d, static_cast<double*>(ws));
   NUMS_LAUNCH_OK();
   lr_fold_kernel<<<(len + 255) / 256, 256, 0, s>>>(static_cast<const double*>(ws), grid, len, out);
   NUMS_LAUNCH_OK();
   return NUMS_OK;
 }
 
+// d for which the dense (bulk-copy) kernel applies: pitch d conflict free, 3 tiles + scratch fit,
+// and the per-CTA fold (8 x (D8 + D8^2) doubles) fits in the ring.
+bool lr_dense_ok(int64_t d) {
+  if (d < 2 || d > 48 || !((d % 16 == 4) || (d % 16 == 12))) return false;
+  const int nb = (int)((d + 7) / 8);
+  const size_t tile_bytes = (size_t)kTileRows * d * sizeof(double);
+  const size_t smem = kDenseStages * tile_bytes + (8 * 64 + nb * 8 + 8) * sizeof(double);
+  return smem <= 227 * 1024 && (size_t)8 * (nb * 8 + nb * 8 * nb * 8) * sizeof(double) <= kDenseStages * tile_bytes;
+}
+
+int dispatch_lr_dense(const LrBlocks& blk, const double* beta, int d, double* out, void* ws, size_t ws_bytes,
+                      cudaStream_t s) {
+  switch ((d + 7) / 8) {
+    case 1: return launch_lr_dense<1>(blk, beta, d, out, ws, ws_bytes, s);
+    case 2: return launch_lr_dense<2>(blk, beta, d, out, ws, ws_bytes, s);
+    case 3: return launch_lr_dense<3>(blk, beta, d, out, ws, ws_bytes, s);
+    case 4: return launch_lr_dense<4>(blk, beta, d, out, ws, ws_bytes, s);
+    case 5: return launch_lr_dense<5>(blk, beta, d, out, ws, ws_bytes, s);
+    case 6: return launch_lr_dense<6>(blk, beta, d, out, ws, ws_bytes, s);
+  }
+  NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "lr_grad_hess: d = %d", d);
+}
+
 template <int NB>
 int launch_lr(const double* X, int64_t ldx, const double* y, const double* beta, int64_t n, int d,
               double* out, void* ws, size_t ws_bytes, cudaStream_t s) {
   constexpr int PITCH = lr_pitch(NB);
-  {
-    // dense fast path: contiguous rows whose pitch is conflict free as is, 3 tiles + scratch fit,
-    // and the per-CTA fold (8 x (D8 + D8^2) doubles) fits in the ring
-    const size_t tile_bytes = (size_t)kTileRows * d * sizeof(double);
-    const size_t smem = kDenseStages * tile_bytes + (8 * 64 + NB * 8 + 8) * sizeof(double);
-    const bool pitch_ok = (d % 16 == 4) || (d % 16 == 12);
-    if (ldx == d && pitch_ok && smem <= 227 * 1024 &&
-        (size_t)8 * (NB * 8 + NB * 8 * NB * 8) * sizeof(double) <= kDenseStages * tile_bytes)
-      return launch_lr_dense<NB>(X, y, beta, n, d, out, ws, ws_bytes, s);
+  if (ldx == d && lr_dense_ok(d)) {
+    LrBlocks blk;
+    memset(&blk, 0, sizeof(blk));
+    blk.count = 1;
+    blk.X[0] = X; blk.y[0] = y; blk.rows[0] = n;
+    blk.tile_begin[0] = 0;
+    blk.tile_begin[1] = (n + kTileRows - 1) / kTileRows;
+    return launch_lr_dense<NB>(blk, beta, d, out, ws, ws_bytes, s);
   }
   const size_t stage_bytes = (size_t)kTileRows * PITCH * sizeof(double);
   int stages = 3;
@@ -493,4 +542,27 @@ extern "C" int nums_lr_grad_hess(int64_t n, int64_t d, const double* X, int64_t 
     case 6: return launch_lr<6>(X, ldx, y, beta, n, (int)d, out, ws, ws_bytes, s);
   }
   NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "lr_grad_hess: d = %lld", (long long)d);
+}
+
+extern "C" int nums_lr_grad_hess_blocks(int nblocks, const double* const* X_host, const double* const* y_host,
+                                        const int64_t* rows_host, int64_t d, const double* beta, double* out,
+                                        void* ws, size_t ws_bytes, void* stream) {
+  using namespace nums;
+  NUMS_REQUIRE(nblocks >= 1 && nblocks <= kMaxLrBlocks, "lr_grad_hess_blocks: 1..%d blocks per call", kMaxLrBlocks);
+  NUMS_REQUIRE(X_host && y_host && rows_host && beta && out, "lr_grad_hess_blocks: null pointer");
+  if (!lr_dense_ok(d))
+    NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "lr_grad_hess_blocks: d = %lld is not served by the dense kernel", (long long)d);
+  LrBlocks blk;
+  memset(&blk, 0, sizeof(blk));
+  blk.count = nblocks;
+  int64_t tiles = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    NUMS_REQUIRE(rows_host[b] >= 1 && X_host[b] && y_host[b], "lr_grad_hess_blocks: block %d is empty", b);
+    NUMS_REQUIRE((reinterpret_cast<uintptr_t>(X_host[b]) & 15u) == 0, "lr_grad_hess_blocks: X block %d is not 16-byte aligned", b);
+    blk.X[b] = X_host[b]; blk.y[b] = y_host[b]; blk.rows[b] = rows_host[b];
+    blk.tile_begin[b] = tiles;
+    tiles += (rows_host[b] + kTileRows - 1) / kTileRows;
+  }
+  blk.tile_begin[nblocks] = tiles;
+  return dispatch_lr_dense(blk, beta, (int)d, out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }

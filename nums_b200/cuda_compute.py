@@ -833,3 +833,28 @@ def lr_grad_hess(X, y, beta):
     LIB.call_ws(LIB.dll.nums_lr_grad_hess, X.device,
                 ((n, d, X.data_ptr(), X.stride(0), y.data_ptr(), beta.data_ptr(), out.data_ptr()), (_stream(),)))
     return out
+
+
+def lr_grad_hess_blocks(x_blocks, y_blocks, beta):
+    """g | H summed over a list of row blocks.  Dense blocks of a supported width go through
+    nums_lr_grad_hess_blocks (16 blocks per launch); anything else block by block."""
+    d = x_blocks[0].shape[1]
+    dense = ((d % 16 in (4, 12)) and d <= 48
+             and all(x.is_contiguous() and x.dtype == torch.float64 and x.data_ptr() % 16 == 0 for x in x_blocks))
+    total = None
+    if dense:
+        ct = _lib.ctypes
+        for lo in range(0, len(x_blocks), 16):
+            xs, ys = x_blocks[lo:lo + 16], y_blocks[lo:lo + 16]
+            out = _empty((d + d * d,), np.float64)
+            xp = (ct.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+            yp = (ct.c_void_p * len(xs))(*[y.data_ptr() for y in ys])
+            rows = (ct.c_int64 * len(xs))(*[x.shape[0] for x in xs])
+            LIB.call_ws(LIB.dll.nums_lr_grad_hess_blocks, xs[0].device,
+                        ((len(xs), xp, yp, rows, d, beta.data_ptr(), out.data_ptr()), (_stream(),)))
+            total = out if total is None else elementwise("add", total, out)
+        return total
+    for x, y in zip(x_blocks, y_blocks):
+        part = lr_grad_hess(x, y, beta)
+        total = part if total is None else elementwise("add", total, part)
+    return total

@@ -149,10 +149,16 @@ class SummaMatmul(object):
             b_panel[j] = buf
         return a_panel, b_panel, [w for w in works if w is not None]
 
-    def run(self, a_blocks, b_blocks):
-        """Returns {(i, j): block} for the C blocks this rank owns."""
+    def run(self, a_blocks, b_blocks, flush_every=None):
+        """Returns {(i, j): block} for the C blocks this rank owns.
+
+        The local updates of `flush_every` consecutive k-steps (default: half the grid) are handed to
+        the system as one deferred chain, so they run as a single grouped GEMM launch that overlaps
+        with the broadcasts of the following steps and touches C only once per flush."""
         shape = (self.bs, self.bs)
         c_blocks = {}
+        if flush_every is None:
+            flush_every = max(1, self.g // 2)
         nxt = self._panels(0, a_blocks, b_blocks)
         for k in range(self.g):
             a_panel, b_panel, works = nxt
@@ -168,8 +174,8 @@ class SummaMatmul(object):
                     prev = c_blocks.get((i, j))
                     c_blocks[(i, j)] = dot if prev is None else self.system.bop(
                         "add", prev, dot, shape, shape, False, False, axes=None, syskwargs=sysk)
-            if hasattr(self.system, "flush"):
-                self.system.flush()   # one grouped launch for this step's C += A(:,k) B(k,:) updates
+            if hasattr(self.system, "flush") and ((k + 1) % flush_every == 0 or k + 1 == self.g):
+                self.system.flush()   # one grouped launch for the C += A(:,k) B(k,:) updates so far
         return c_blocks
 
 
@@ -216,8 +222,8 @@ def tsqr_q(system, x_block, r_inv, entry, grid_shape):
 def newton_lr(system, comm, x_blocks, y_blocks, d, tol, max_iter, grad_hess):
     """Newton iterations (glms.py:362-372) on row-sharded data; returns (beta, iterations).
 
-    ``grad_hess(X_block, y_block, beta) -> 1-D buffer of d + d*d`` is the fused kernel
-    (cuda_compute.lr_grad_hess) or, in the CPU tests, its NumPy statement.  The all-reduce of that
+    ``grad_hess(x_blocks, y_blocks, beta) -> 1-D buffer of d + d*d`` (summed over the blocks) is the
+    fused kernel (cuda_compute.lr_grad_hess_blocks) or, in the CPU tests, its NumPy statement.  The all-reduce of that
     buffer replaces the reference's gathers (``sum_reduce`` of G gradients, the (d, d) add chain).
     """
     beta = system.new_block("zeros", (0,), {"shape": (d,), "block_shape": (d,), "dtype": "float64"},
@@ -226,11 +232,7 @@ def newton_lr(system, comm, x_blocks, y_blocks, d, tol, max_iter, grad_hess):
     iters = 0
     for _ in range(max_iter):
         iters += 1
-        acc = None
-        for xb, yb in zip(x_blocks, y_blocks):
-            part = grad_hess(xb, yb, beta)
-            acc = part if acc is None else system.bop("add", acc, part, (d + d * d,), (d + d * d,), False, False,
-                                                      axes=None, syskwargs=sk)
+        acc = grad_hess(x_blocks, y_blocks, beta)    # g | H summed over this rank's row blocks
         comm.all_reduce_sum(acc)
         g = acc[:d]
         h = acc[d:].reshape(d, d) if isinstance(acc, np.ndarray) else acc[d:].view(d, d)

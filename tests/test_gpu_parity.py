@@ -642,3 +642,20 @@ def test_svd(cuda_system, oracle, n):
         assert rel_fro((u * s) @ vt, A) <= 1e-10
         assert np.linalg.norm(u.T @ u - np.eye(n)) <= 1e-10 * n
         assert np.linalg.norm(vt @ vt.T - np.eye(n)) <= 1e-10 * n
+
+
+def test_lr_grad_hess_blocks(cuda_system):
+    from nums_b200 import cuda_compute
+    rng = np.random.default_rng(72)
+    for d, rows in ((28, [1000, 257, 4096, 31]), (12, [300] * 20), (8, [500, 600])):
+        xs = [rng.standard_normal((r, d)) for r in rows]
+        ys = [(rng.random(r) < 0.5).astype(np.float64) for r in rows]
+        beta = rng.standard_normal(d) / np.sqrt(d)
+        X, y = np.concatenate(xs), np.concatenate(ys)
+        mu = 1.0 / (1.0 + np.exp(-(X @ beta)))
+        g = X.T @ (mu - y)
+        H = X.T @ ((mu * (1 - mu))[:, None] * X)
+        out = cuda_system.get(cuda_compute.lr_grad_hess_blocks([cuda_system.put(x) for x in xs],
+                                                               [cuda_system.put(v) for v in ys], cuda_system.put(beta)))
+        assert rel_fro(out[:d], g) <= GEMM_TOL
+        assert rel_fro(out[d:].reshape(d, d), H) <= GEMM_TOL

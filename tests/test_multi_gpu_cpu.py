@@ -22,6 +22,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _np_grad_hess_blocks(xs, ys, beta):
+    return sum(_np_grad_hess(x, y, beta) for x, y in zip(xs, ys))
+
+
 def _np_grad_hess(X, y, beta):
     mu = 1.0 / (1.0 + np.exp(-(X @ beta)))
     g = X.T @ (mu - y)
@@ -64,7 +68,7 @@ def _worker(rank, world, port, results):
         yl = (rng.random(400) < 0.5).astype(np.float64)
         xs = [Xl[i * 50:(i + 1) * 50] for i in range(8) if i % world == rank]
         ys = [yl[i * 50:(i + 1) * 50] for i in range(8) if i % world == rank]
-        beta, iters = multi_gpu.newton_lr(system, comm, xs, ys, 5, 1e-10, 6, _np_grad_hess)
+        beta, iters = multi_gpu.newton_lr(system, comm, xs, ys, 5, 1e-10, 6, _np_grad_hess_blocks)
         out["beta"], out["iters"] = np.asarray(beta), iters
         results[rank] = out
     finally:
