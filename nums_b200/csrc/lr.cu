@@ -32,9 +32,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
 }
 
 // pitch == 4 (mod 16) doubles => the (row = t, feature = g) fragment reads are conflict free
@@ -262,16 +262,18 @@ __device__ __forceinline__ int lr_find_block(const LrBlocks& blk, int64_t tile) 
   return b;
 }
 
-template <int NB>
+template <int D>   // number of features, compile time: pass 1 becomes straight-line code
 __global__ void __launch_bounds__(kDenseThreads, 1)
-lr_grad_hess_dense_kernel(const __grid_constant__ LrBlocks blk, const double* __restrict__ beta, int d,
+lr_grad_hess_dense_kernel(const __grid_constant__ LrBlocks blk, const double* __restrict__ beta,
                           double* __restrict__ partial) {
+  constexpr int d = D;
+  constexpr int NB = (D + 7) / 8;
   constexpr int NTRI = NB * (NB + 1) / 2;
   extern __shared__ __align__(128) unsigned char lr_smem[];
   const int tile_doubles = kTileRows * d;
   double* ring = reinterpret_cast<double*>(lr_smem);                       // kDenseStages tiles
-  double* scratch = ring + (size_t)kDenseStages * tile_doubles;            // 8 warps x (32 s + 32 e)
-  double* bsm = scratch + 8 * 64;                                          // beta, zero padded to NB*8
+  double* scratch = ring + (size_t)kDenseStages * tile_doubles;            // 8 warps x 2 buffers x (32 s + 32 e)
+  double* bsm = scratch + 8 * 128;                                          // beta, zero padded to NB*8
   uint64_t* full = reinterpret_cast<uint64_t*>(bsm + NB * 8);              // data landed (producer -> consumers)
   uint64_t* empty = full + kDenseStages;                                   // slot released (8 warps -> producer)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -292,12 +294,11 @@ lr_grad_hess_dense_kernel(const __grid_constant__ LrBlocks blk, const double* __
   const int64_t ntiles = blk.tile_begin[blk.count];
   const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  double hacc[NTRI][2];
-  double gacc[NB];
+  // Two accumulator sets used by alternating row groups: consecutive DMMAs into the same
+  // accumulator are then 2 x NTRI instructions apart, which covers the DMMA result latency.
+  double hacc[2][NTRI][2];
 #pragma unroll
-  for (int i = 0; i < NTRI; ++i) hacc[i][0] = hacc[i][1] = 0.0;
-#pragma unroll
-  for (int i = 0; i < NB; ++i) gacc[i] = 0.0;
+  for (int i = 0; i < NTRI; ++i) hacc[0][i][0] = hacc[0][i][1] = hacc[1][i][0] = hacc[1][i][1] = 0.0;
 
   if (warp == 8) {
     // ===== producer warp: one lane feeds the ring with bulk (TMA) copies =====
@@ -318,76 +319,98 @@ lr_grad_hess_dense_kernel(const __grid_constant__ LrBlocks blk, const double* __
     }
   } else {
     // ===== consumer warps: 32 rows each per tile, free-running (no CTA barrier per tile) =====
-    double* my_s = scratch + warp * 64;
-    double* my_e = my_s + 32;
-    // (y value, validity) of this lane's row in a given tile
+    // Software pipelined: while the tensor pipe works through the rank-4 updates of tile i
+    // (pass 2), the same warp already evaluates z / sigmoid for tile i + 1 (pass 1); the two are
+    // independent instruction streams in one basic block, so the long FP64 latency chains of
+    // pass 1 (dot product, exp, divide) hide behind the 16-cycle DMMA cadence.
+    double* scr = scratch + warp * 128;          // [buffer][s: 32 | e: 32]
+    const int gcol_block = d >> 3, gcol_lane = d & 7;   // padding column that carries e (gradient)
     auto fetch_y = [&](int64_t tile, bool& valid) -> double {
       const int b = lr_find_block(blk, tile);
       const int64_t row = (tile - blk.tile_begin[b]) * kTileRows + warp * 32 + lane;
       valid = row < blk.rows[b];
       return valid ? blk.y[b][row] : 0.0;
     };
-    bool valid_cur = false;
-    double y_cur = my_tiles > 0 ? fetch_y(blockIdx.x, valid_cur) : 0.0;
+    // pass 1 is cut into slices so that it can be issued between the MMA groups of pass 2:
+    // slice q accumulates features [4q, 4q + 4) of this lane's row into four partial sums.
+    auto dot_slice = [&](const double* xr, int q, double (&z)[4]) {
+      const int j = 4 * q;
+      if (j + 4 <= D) {
+        const double2 v = *reinterpret_cast<const double2*>(xr + j);
+        const double2 w = *reinterpret_cast<const double2*>(xr + j + 2);
+        z[0] = fma(v.x, bsm[j], z[0]);
+        z[1] = fma(v.y, bsm[j + 1], z[1]);
+        z[2] = fma(w.x, bsm[j + 2], z[2]);
+        z[3] = fma(w.y, bsm[j + 3], z[3]);
+      } else if (j + 2 <= D) {
+        const double2 v = *reinterpret_cast<const double2*>(xr + j);
+        z[0] = fma(v.x, bsm[j], z[0]);
+        z[1] = fma(v.y, bsm[j + 1], z[1]);
+      }
+    };
+    constexpr int kSlices = (D + 3) / 4;
+    auto finish = [&](const double (&z)[4], double yv, bool valid, double* out_s, double* out_e) {
+      const double mu = 1.0 / (1.0 + exp(-((z[0] + z[1]) + (z[2] + z[3]))));
+      out_s[lane] = valid ? mu * (1.0 - mu) : 0.0;   // rows past the end may hold stale data: weight 0
+      out_e[lane] = valid ? mu - yv : 0.0;
+    };
+
+    if (my_tiles > 0) {
+      bool valid0 = false;
+      const double y0 = fetch_y(blockIdx.x, valid0);
+      mbar_wait(&full[0], 0u);
+      double z[4] = {0.0, 0.0, 0.0, 0.0};
+      const double* xr = ring + (size_t)warp * 32 * d + lane * d;
+#pragma unroll
+      for (int q = 0; q < kSlices; ++q) dot_slice(xr, q, z);
+      finish(z, y0, valid0, scr, scr + 32);
+      __syncwarp();
+    }
     for (int64_t i = 0; i < my_tiles; ++i) {
       const int slot = (int)(i % kDenseStages);
-      mbar_wait(&full[slot], (uint32_t)((i / kDenseStages) & 1));
-      const double* xs = ring + (size_t)slot * tile_doubles + (size_t)warp * 32 * d;
-
-      // pass 1: one row per lane
-      {
-        const double* xr = xs + lane * d;
-        double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
-        int j = 0;
-        for (; j + 4 <= d; j += 4) {
-          const double2 v = *reinterpret_cast<const double2*>(xr + j);
-          const double2 w = *reinterpret_cast<const double2*>(xr + j + 2);
-          z0 = fma(v.x, bsm[j], z0);
-          z1 = fma(v.y, bsm[j + 1], z1);
-          z2 = fma(w.x, bsm[j + 2], z2);
-          z3 = fma(w.y, bsm[j + 3], z3);
-        }
-        for (; j < d; j += 2) {
-          const double2 v = *reinterpret_cast<const double2*>(xr + j);
-          z0 = fma(v.x, bsm[j], z0);
-          z1 = fma(v.y, bsm[j + 1], z1);
-        }
-        const bool valid = valid_cur;
-        const double mu = 1.0 / (1.0 + exp(-((z0 + z1) + (z2 + z3))));
-        my_s[lane] = valid ? mu * (1.0 - mu) : 0.0;   // rows past the end may hold stale data: weight 0
-        my_e[lane] = valid ? mu - y_cur : 0.0;
-      }
-      // y of the next tile: issued now, consumed after pass 2 (latency hidden behind the MMAs)
+      const bool has_next = i + 1 < my_tiles;
+      const int nslot = has_next ? (int)((i + 1) % kDenseStages) : slot;
       bool valid_next = false;
-      const double y_next = (i + 1 < my_tiles) ? fetch_y((int64_t)blockIdx.x + (i + 1) * gridDim.x, valid_next) : 0.0;
-      __syncwarp();
+      const double y_next = has_next ? fetch_y((int64_t)blockIdx.x + (i + 1) * gridDim.x, valid_next) : 0.0;
+      if (has_next) mbar_wait(&full[nslot], (uint32_t)(((i + 1) / kDenseStages) & 1));
+      const double* xs = ring + (size_t)slot * tile_doubles + (size_t)warp * 32 * d;
+      const double* xr_next = ring + (size_t)nslot * tile_doubles + (size_t)warp * 32 * d + lane * d;
+      const double* cur_s = scr + (i & 1) * 64;
+      const double* cur_e = cur_s + 32;
+      double* nxt_s = scr + ((i + 1) & 1) * 64;
+      double z[4] = {0.0, 0.0, 0.0, 0.0};
 
-      // pass 2: rank-4 updates
+      // pass 2 of tile i: H += x (s x)^T with DMMA; the padding column d of the B operand carries e,
+      // so the gradient X^T e accumulates in column d of the same tensor-pipe product.  Between the
+      // groups, slices of pass 1 of tile i + 1 (same tile again when there is none: result unused).
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const double s = my_s[4 * q + t];
-        const double e = my_e[4 * q + t];
+        const double sv = cur_s[4 * q + t];
+        const double ev = cur_e[4 * q + t];
         const double* xr = xs + (4 * q + t) * d + g;
-        double xf[NB], af[NB];
+        double xf[NB], bf[NB];
 #pragma unroll
         for (int bi = 0; bi < NB; ++bi) {
           xf[bi] = (8 * bi + g < d) ? xr[8 * bi] : 0.0;
-          af[bi] = s * xf[bi];
-          gacc[bi] = fma(e, xf[bi], gacc[bi]);
+          bf[bi] = sv * xf[bi];
         }
+        if (g == gcol_lane) bf[NB - 1] = ev;   // gcol_block == NB - 1 for every d this kernel serves
+        if (q < kSlices) dot_slice(xr_next, q, z);
         int idx = 0;
 #pragma unroll
         for (int bi = 0; bi < NB; ++bi)
 #pragma unroll
           for (int bj = bi; bj < NB; ++bj) {
-            dmma884(hacc[idx], af[bi], xf[bj]);
+            dmma884(hacc[q & 1][idx], xf[bi], bf[bj]);
             ++idx;
           }
       }
+#pragma unroll
+      for (int q = 8; q < kSlices; ++q) dot_slice(xr_next, q, z);
+      finish(z, y_next, valid_next && has_next, nxt_s, nxt_s + 32);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[slot]);   // this warp is done with the slot
-      y_cur = y_next;
-      valid_cur = valid_next;
+      (void)gcol_block;
     }
   }
   __syncthreads();
@@ -400,21 +423,14 @@ lr_grad_hess_dense_kernel(const __grid_constant__ LrBlocks blk, const double* __
   __syncthreads();
   if (warp < 8) {
     double* mine = red + warp * PER_WARP;
-#pragma unroll
-    for (int bi = 0; bi < NB; ++bi) {
-      double v = gacc[bi];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (t == 0) mine[8 * bi + g] = v;
-    }
     int idx = 0;
 #pragma unroll
     for (int bi = 0; bi < NB; ++bi)
 #pragma unroll
       for (int bj = bi; bj < NB; ++bj) {
         double* h = mine + D8 + (8 * bi + g) * D8 + 8 * bj + 2 * t;
-        h[0] = hacc[idx][0];
-        h[1] = hacc[idx][1];
+        h[0] = hacc[0][idx][0] + hacc[1][idx][0];
+        h[1] = hacc[0][idx][1] + hacc[1][idx][1];
         ++idx;
       }
   }
@@ -422,7 +438,7 @@ lr_grad_hess_dense_kernel(const __grid_constant__ LrBlocks blk, const double* __
   double* out = partial + (size_t)blockIdx.x * (d + d * d);
   for (int i = threadIdx.x; i < d + d * d; i += kDenseThreads) {
     int src;
-    if (i < d) src = i;
+    if (i < d) src = D8 + i * D8 + d;     // gradient: column d (the padding column that carried e)
     else {
       const int r = (i - d) / d, c = (i - d) - r * d;
       src = (r <= c) ? D8 + r * D8 + c : D8 + c * D8 + r;
@@ -443,44 +459,47 @@ lr_fold_kernel(const double* __restrict__ partial, int parts, int len, double* _
   out[i] = acc;
 }
 
-template <int NB>
-int launch_lr_dense(const LrBlocks& blk, const double* beta, int d, double* out, void* ws, size_t ws_bytes,
+template <int D>
+int launch_lr_dense(const LrBlocks& blk, const double* beta, double* out, void* ws, size_t ws_bytes,
                     cudaStream_t s) {
+  constexpr int d = D;
+  constexpr int NB = (D + 7) / 8;
   const size_t tile_bytes = (size_t)kTileRows * d * sizeof(double);
-  const size_t smem = kDenseStages * tile_bytes + (8 * 64 + NB * 8) * sizeof(double) + 2 * kDenseStages * sizeof(uint64_t);
+  const size_t smem = kDenseStages * tile_bytes + (8 * 128 + NB * 8) * sizeof(double) + 2 * kDenseStages * sizeof(uint64_t);
   const int len = d + d * d;
   const int64_t ntiles = blk.tile_begin[blk.count];
   int grid = sm_count();
   if (grid > ntiles) grid = (int)ntiles;
   if (grid < 1) grid = 1;
   NUMS_NEED_WS((size_t)grid * len * sizeof(double), ws_bytes);
-  NUMS_CUDA_OK(cudaFuncSetAttribute(lr_grad_hess_dense_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lr_grad_hess_dense_kernel<NB><<<grid, kDenseThreads, smem, s>>>(blk, beta, d, static_cast<double*>(ws));
+  NUMS_CUDA_OK(cudaFuncSetAttribute(lr_grad_hess_dense_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lr_grad_hess_dense_kernel<D><<<grid, kDenseThreads, smem, s>>>(blk, beta, static_cast<double*>(ws));
   NUMS_LAUNCH_OK();
   lr_fold_kernel<<<(len + 255) / 256, 256, 0, s>>>(static_cast<const double*>(ws), grid, len, out);
   NUMS_LAUNCH_OK();
   return NUMS_OK;
 }
 
-// d for which the dense (bulk-copy) kernel applies: pitch d conflict free, 3 tiles + scratch fit,
-// and the per-CTA fold (8 x (D8 + D8^2) doubles) fits in the ring.
+// d for which the dense (bulk-copy) kernel applies: pitch d conflict free (d == 4 or 12 mod 16, which
+// also leaves padding column d free for the gradient), 3 tiles + scratch fit, and the per-CTA fold
+// (8 x (D8 + D8^2) doubles) fits in the ring.
 bool lr_dense_ok(int64_t d) {
-  if (d < 2 || d > 48 || !((d % 16 == 4) || (d % 16 == 12))) return false;
+  if (!(d == 4 || d == 12 || d == 20 || d == 28 || d == 36 || d == 44)) return false;
   const int nb = (int)((d + 7) / 8);
   const size_t tile_bytes = (size_t)kTileRows * d * sizeof(double);
-  const size_t smem = kDenseStages * tile_bytes + (8 * 64 + nb * 8 + 8) * sizeof(double);
+  const size_t smem = kDenseStages * tile_bytes + (8 * 128 + nb * 8 + 8) * sizeof(double);
   return smem <= 227 * 1024 && (size_t)8 * (nb * 8 + nb * 8 * nb * 8) * sizeof(double) <= kDenseStages * tile_bytes;
 }
 
 int dispatch_lr_dense(const LrBlocks& blk, const double* beta, int d, double* out, void* ws, size_t ws_bytes,
                       cudaStream_t s) {
-  switch ((d + 7) / 8) {
-    case 1: return launch_lr_dense<1>(blk, beta, d, out, ws, ws_bytes, s);
-    case 2: return launch_lr_dense<2>(blk, beta, d, out, ws, ws_bytes, s);
-    case 3: return launch_lr_dense<3>(blk, beta, d, out, ws, ws_bytes, s);
-    case 4: return launch_lr_dense<4>(blk, beta, d, out, ws, ws_bytes, s);
-    case 5: return launch_lr_dense<5>(blk, beta, d, out, ws, ws_bytes, s);
-    case 6: return launch_lr_dense<6>(blk, beta, d, out, ws, ws_bytes, s);
+  switch (d) {
+    case 4: return launch_lr_dense<4>(blk, beta, out, ws, ws_bytes, s);
+    case 12: return launch_lr_dense<12>(blk, beta, out, ws, ws_bytes, s);
+    case 20: return launch_lr_dense<20>(blk, beta, out, ws, ws_bytes, s);
+    case 28: return launch_lr_dense<28>(blk, beta, out, ws, ws_bytes, s);
+    case 36: return launch_lr_dense<36>(blk, beta, out, ws, ws_bytes, s);
+    case 44: return launch_lr_dense<44>(blk, beta, out, ws, ws_bytes, s);
   }
   NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "lr_grad_hess: d = %d", d);
 }
@@ -496,7 +515,7 @@ int launch_lr(const double* X, int64_t ldx, const double* y, const double* beta,
     blk.X[0] = X; blk.y[0] = y; blk.rows[0] = n;
     blk.tile_begin[0] = 0;
     blk.tile_begin[1] = (n + kTileRows - 1) / kTileRows;
-    return launch_lr_dense<NB>(blk, beta, d, out, ws, ws_bytes, s);
+    return dispatch_lr_dense(blk, beta, d, out, ws, ws_bytes, s);
   }
   const size_t stage_bytes = (size_t)kTileRows * PITCH * sizeof(double);
   int stages = 3;
