@@ -337,6 +337,167 @@ splitk_fold_kernel(const double* __restrict__ partial, int splits, int64_t M, in
 }
 
 // ======================================================================================
+// Skinny A^T B: C[M,N] = A^T B with M, N <= 32 and a very long contraction (K rows)
+// ======================================================================================
+// The shapes of the LR Hessian X^T (s X) and gradient-like products through the unfused interface
+// path (glms.py:232-238: (28, n_b) . (n_b, 28)) and of small Gram matrices.  A 128x128 output tile
+// would waste 95 % of the MMA work there; instead every CTA streams 256-row chunks of A (K x M) and
+// B (K x N) through a cp.async ring and each warp turns its 32 rows into eight rank-4 DMMA updates
+// of the whole (<= 4 x 4 blocks of 8 x 8) output, i.e. the kernel is HBM bound: 8 (M + N) bytes per
+// row.  Per-CTA partials are folded by splitk_fold_kernel (deterministic order).
+constexpr int kSkinnyStages = 3;
+
+__host__ __device__ constexpr int skinny_pitch(int cols) {   // smallest pitch >= cols with pitch % 16 in {4, 12}
+  int p = cols;
+  while (!((p % 16 == 4) || (p % 16 == 12))) ++p;
+  return p;
+}
+
+template <int MB, int NB, int kSkinnyRows>   // kSkinnyRows = 256 or 128 rows per chunk (shared-memory budget)
+__global__ void __launch_bounds__(256, 1)
+dgemm_tn_skinny_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                       int M, int N, int64_t K, int same, double* __restrict__ partial) {
+  constexpr int PA = skinny_pitch(MB * 8), PB = skinny_pitch(NB * 8);
+  extern __shared__ __align__(16) double sk_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  double* ringA = sk_smem;
+  double* ringB = sk_smem + (size_t)kSkinnyStages * kSkinnyRows * PA;
+  const int total_doubles = kSkinnyStages * kSkinnyRows * (PA + (same ? 0 : PB));
+  for (int i = threadIdx.x; i < total_doubles; i += 256) sk_smem[i] = 0.0;   // padding columns stay zero
+  __syncthreads();
+
+  double acc[MB][NB][2];
+#pragma unroll
+  for (int i = 0; i < MB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int64_t nchunks = (K + kSkinnyRows - 1) / kSkinnyRows;
+  auto load_rows = [&](double* dst, int pitch, const double* src, int64_t ld, int cols, int64_t r0) {
+    // each warp copies rows warp, warp + 8, ...; lanes cover the 16-byte pieces of a row
+    const int pieces = cols >> 1;
+    for (int r = warp; r < kSkinnyRows; r += 8) {
+      const int64_t gr = r0 + r;
+      const bool in = gr < K;
+      for (int c = lane; c < pieces; c += 32)
+        cp_async16(dst + r * pitch + 2 * c, in ? src + gr * ld + 2 * c : src, in ? 16 : 0);
+    }
+  };
+  auto load_chunk = [&](int slot, int64_t chunk) {
+    const int64_t r0 = chunk * kSkinnyRows;
+    load_rows(ringA + (size_t)slot * kSkinnyRows * PA, PA, A, lda, M, r0);
+    if (!same) load_rows(ringB + (size_t)slot * kSkinnyRows * PB, PB, B, ldb, N, r0);
+  };
+
+  int64_t chunk = blockIdx.x;
+  for (int s = 0; s < kSkinnyStages - 1; ++s) {
+    const int64_t c = chunk + (int64_t)s * gridDim.x;
+    if (c < nchunks) load_chunk(s, c);
+    cp_async_commit();
+  }
+  int slot = 0;
+  for (; chunk < nchunks; chunk += gridDim.x) {
+    cp_async_wait<kSkinnyStages - 2>();
+    __syncthreads();
+    {
+      const int64_t nxt = chunk + (int64_t)(kSkinnyStages - 1) * gridDim.x;
+      int nslot = slot + kSkinnyStages - 1;
+      if (nslot >= kSkinnyStages) nslot -= kSkinnyStages;
+      if (nxt < nchunks) load_chunk(nslot, nxt);
+      cp_async_commit();
+    }
+    constexpr int kWarpRows = kSkinnyRows / 8;
+    const double* a = ringA + (size_t)slot * kSkinnyRows * PA + (size_t)warp * kWarpRows * PA;
+    const double* b = same ? a : ringB + (size_t)slot * kSkinnyRows * PB + (size_t)warp * kWarpRows * PB;
+    const int pb = same ? PA : PB;
+#pragma unroll
+    for (int q = 0; q < kWarpRows / 4; ++q) {
+      double af[MB], bf[NB];
+#pragma unroll
+      for (int i = 0; i < MB; ++i) af[i] = a[(4 * q + t) * PA + 8 * i + g];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) bf[j] = b[(4 * q + t) * pb + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) dmma884(acc[i][j], af[i], bf[j]);
+    }
+    ++slot;
+    if (slot == kSkinnyStages) slot = 0;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // CTA fold: 8 warps -> one (MB*8) x (NB*8) tile in shared memory, then the M x N corner goes out
+  constexpr int TM = MB * 8, TN = NB * 8;
+  double* red = sk_smem;   // 8 * TM * TN doubles <= 64 KB, the ring is larger
+  double* mine = red + warp * TM * TN;
+#pragma unroll
+  for (int i = 0; i < MB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      mine[(8 * i + g) * TN + 8 * j + 2 * t] = acc[i][j][0];
+      mine[(8 * i + g) * TN + 8 * j + 2 * t + 1] = acc[i][j][1];
+    }
+  __syncthreads();
+  double* out = partial + (size_t)blockIdx.x * M * N;
+  for (int e = threadIdx.x; e < M * N; e += 256) {
+    const int r = e / N, c = e - r * N;
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w * TM * TN + r * TN + c];
+    out[e] = v;
+  }
+}
+
+template <int MB, int NB, int kSkinnyRows>
+int launch_skinny_rows(const double* A, int64_t lda, const double* B, int64_t ldb, int M, int N, int64_t K,
+                       const double* Cin, int64_t ldcin, double* C, int64_t ldc, void* ws, size_t ws_bytes,
+                       cudaStream_t s) {
+  const int same = (A == B && lda == ldb && M == N) ? 1 : 0;
+  constexpr int PA = skinny_pitch(MB * 8), PB = skinny_pitch(NB * 8);
+  const size_t smem = (size_t)kSkinnyStages * kSkinnyRows * (PA + (same ? 0 : PB)) * sizeof(double);
+  const int64_t nchunks = (K + kSkinnyRows - 1) / kSkinnyRows;
+  int grid = sm_count();
+  if (grid > nchunks) grid = (int)nchunks;
+  NUMS_NEED_WS((size_t)grid * M * N * sizeof(double), ws_bytes);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(dgemm_tn_skinny_kernel<MB, NB, kSkinnyRows>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dgemm_tn_skinny_kernel<MB, NB, kSkinnyRows><<<grid, 256, smem, s>>>(A, lda, B, ldb, M, N, K, same,
+                                                                     static_cast<double*>(ws));
+  NUMS_LAUNCH_OK();
+  splitk_fold_kernel<<<blocks_for((int64_t)M * N, 256), 256, 0, s>>>(static_cast<const double*>(ws), grid, M, N, Cin,
+                                                                     ldcin, C, ldc);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
+template <int MB, int NB>
+int launch_skinny(const double* A, int64_t lda, const double* B, int64_t ldb, int M, int N, int64_t K,
+                  const double* Cin, int64_t ldcin, double* C, int64_t ldc, void* ws, size_t ws_bytes,
+                  cudaStream_t s) {
+  const bool same = (A == B && lda == ldb && M == N);
+  constexpr int PA = skinny_pitch(MB * 8), PB = skinny_pitch(NB * 8);
+  const size_t big = (size_t)kSkinnyStages * 256 * (PA + (same ? 0 : PB)) * sizeof(double);
+  if (big <= 224 * 1024)
+    return launch_skinny_rows<MB, NB, 256>(A, lda, B, ldb, M, N, K, Cin, ldcin, C, ldc, ws, ws_bytes, s);
+  return launch_skinny_rows<MB, NB, 128>(A, lda, B, ldb, M, N, K, Cin, ldcin, C, ldc, ws, ws_bytes, s);
+}
+
+int run_skinny(const double* A, int64_t lda, const double* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+               const double* Cin, int64_t ldcin, double* C, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const int mb = (int)((M + 7) / 8), nb = (int)((N + 7) / 8);
+#define NUMS_SKINNY(MBv, NBv) \
+  if (mb == MBv && nb == NBv) return launch_skinny<MBv, NBv>(A, lda, B, ldb, (int)M, (int)N, K, Cin, ldcin, C, ldc, ws, ws_bytes, s)
+  NUMS_SKINNY(1, 1); NUMS_SKINNY(1, 2); NUMS_SKINNY(1, 3); NUMS_SKINNY(1, 4);
+  NUMS_SKINNY(2, 1); NUMS_SKINNY(2, 2); NUMS_SKINNY(2, 3); NUMS_SKINNY(2, 4);
+  NUMS_SKINNY(3, 1); NUMS_SKINNY(3, 2); NUMS_SKINNY(3, 3); NUMS_SKINNY(3, 4);
+  NUMS_SKINNY(4, 1); NUMS_SKINNY(4, 2); NUMS_SKINNY(4, 3); NUMS_SKINNY(4, 4);
+#undef NUMS_SKINNY
+  NUMS_FAIL(NUMS_ERR_INVALID, "skinny gemm: bad block counts %d x %d", mb, nb);
+}
+
+// ======================================================================================
 // Generic tiled GEMM (any arithmetic dtype, any alignment) -- correctness path
 // ======================================================================================
 template <typename T>
@@ -713,6 +874,8 @@ int run_gemm_typed(int ta, int tb, int64_t M, int64_t N, int64_t K, const T* A, 
   }
   if constexpr (std::is_same<T, double>::value) {
     const bool aligned = dmma_operand_ok(A, lda) && dmma_operand_ok(B, ldb);
+    if (aligned && ta && !tb && M <= 32 && N <= 32 && M % 2 == 0 && N % 2 == 0 && K >= 8192)
+      return run_skinny(A, lda, B, ldb, M, N, K, Cin, ldc, C, ldc, ws, ws_bytes, s);
     const bool worthwhile = M * N >= 32 * 32 || K >= 4096;
     if (aligned && worthwhile)
       return run_dgemm(ta, tb, M, N, K, A, lda, B, ldb, Cin, ldc, C, ldc, ws, ws_bytes, s);

@@ -458,7 +458,8 @@ def _tdot(system, oracle, a, b, axes=1, a_T=False, b_T=False):
 
 @pytest.mark.parametrize("mnk", [(128, 128, 16), (128, 128, 64), (256, 384, 128), (100, 130, 70), (129, 127, 33),
                                  (32, 32, 4096), (28, 28, 20000), (64, 2, 10), (2, 64, 10), (512, 512, 512),
-                                 (1000, 28, 28), (2048, 128, 128)])
+                                 (1000, 28, 28), (2048, 128, 128), (32, 28, 50000), (8, 30, 10000), (2, 2, 100000),
+                                 (28, 28, 8191), (28, 28, 8193)])
 def test_tensordot_f64_matrix(cuda_system, oracle, mnk):
     m, n, k = mnk
     rng = np.random.default_rng(51)
