@@ -453,16 +453,19 @@ def run_gpu(args):
         summa = multi_gpu.SummaMatmul(system, comm, GRID, BLOCK, like)
         mine_a = {e: system.put(v) for e, v in a_host.items() if summa.owner_a(*e) == rank}
         mine_b = {e: system.put(v) for e, v in b_host.items() if summa.owner_b(*e) == rank}
+        packed = summa.pack(mine_a, mine_b)      # resident layout: one contiguous panel per k
+        del mine_a, mine_b
 
         def step_resident():
-            return summa.run(mine_a, mine_b, flush_every=1)
+            return summa.run(packed)
 
         def step_e2e():
             la = {e: system.put(v) for e, v in a_host.items() if summa.owner_a(*e) == rank}
             lb = {e: system.put(v) for e, v in b_host.items() if summa.owner_b(*e) == rank}
-            c = summa.run(la, lb, flush_every=1)
+            c = summa.run(la, lb)
             return {e: system.get(v) for e, v in c.items()}
-        parallelism = "SUMMA on a %dx%d device grid, NCCL broadcasts of A(:,k)/B(k,:) blocks" % (pr, pc)
+        parallelism = ("SUMMA on a %dx%d device grid: one NCCL broadcast of the A(:,k) panel per device row and of the "
+                       "B(k,:) panel per device column per step, prefetched behind the grouped local GEMM" % (pr, pc))
 
     # ---- timed: HBM-resident ---------------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -509,7 +512,7 @@ def run_gpu(args):
         if world == 1:
             c_dev = system.get((A @ B).blocks[0, 0].oid)
         else:
-            c_all = summa.run(mine_a, mine_b)
+            c_all = summa.run(packed)
             key = sorted(c_all)[0]
             c_dev = system.get(c_all[key])
         i, j = (0, 0) if world == 1 else key
@@ -518,12 +521,12 @@ def run_gpu(args):
             ref += a_host[(i, k)] @ b_host[(k, j)]
         verified = float(np.linalg.norm(c_dev - ref) / np.linalg.norm(ref))
     elif world > 1:
-        summa.run(mine_a, mine_b)      # collective: every rank takes part in the verification pass
+        summa.run(packed)              # collective: every rank takes part in the verification pass
     sync_all()
 
     sharded = None
     if world > 1 and not args.skip_workloads:
-        del mine_a, mine_b
+        del packed
         torch.cuda.empty_cache()
         sharded = sharded_workloads(system, comm, quick=args.quick)   # collective: all ranks
 

@@ -131,41 +131,57 @@ class SummaMatmul(object):
     def owner_c(self, i, j):
         return (i % self.pr) * self.pc + (j % self.pc)
 
-    def _panels(self, k, a_blocks, b_blocks):
-        """Start the broadcasts of step k; returns (A panel dict, B panel dict, pending works)."""
+    def pack(self, a_blocks, b_blocks):
+        """Stack this rank's blocks into one contiguous panel per k, so that a SUMMA step needs ONE
+        broadcast per operand instead of one per block: panels[0][k] holds A(i, k) for i in my_i
+        (owned when k mod pc == c), panels[1][k] holds B(k, j) for j in my_j (owned when k mod pr == r)."""
+        def stack(blocks):
+            first = blocks[0]
+            if isinstance(first, np.ndarray):
+                return np.stack(blocks)
+            out = torch.empty((len(blocks),) + tuple(first.shape), dtype=first.dtype, device=first.device)
+            for idx, blk in enumerate(blocks):
+                out[idx].copy_(blk)      # device-to-device placement copy (plumbing, not arithmetic)
+            return out
+        pa = {k: stack([a_blocks[(i, k)] for i in self.my_i]) for k in range(self.g) if k % self.pc == self.c}
+        pb = {k: stack([b_blocks[(k, j)] for j in self.my_j]) for k in range(self.g) if k % self.pr == self.r}
+        return pa, pb
+
+    def _panels(self, k, packed):
+        """Start the (at most two) broadcasts of step k; returns (A panel, B panel, pending works)."""
+        pa, pb = packed
         works = []
-        a_panel, b_panel = {}, {}
-        for i in self.my_i:
-            src = self.owner_a(i, k)
-            buf = a_blocks[(i, k)] if src == self.comm.rank else _empty_like_block(self.system, (self.bs, self.bs), self.like)
-            if self.pc > 1:
-                works.append(self.comm.broadcast(buf, src, self.row_groups[self.r], async_op=True))
-            a_panel[i] = buf
-        for j in self.my_j:
-            src = self.owner_b(k, j)
-            buf = b_blocks[(k, j)] if src == self.comm.rank else _empty_like_block(self.system, (self.bs, self.bs), self.like)
-            if self.pr > 1:
-                works.append(self.comm.broadcast(buf, src, self.col_groups[self.c], async_op=True))
-            b_panel[j] = buf
+        src_a = self.r * self.pc + (k % self.pc)
+        shape_a = (len(self.my_i), self.bs, self.bs)
+        buf_a = pa[k] if src_a == self.comm.rank else _empty_like_block(self.system, shape_a, self.like)
+        if self.pc > 1:
+            works.append(self.comm.broadcast(buf_a, src_a, self.row_groups[self.r], async_op=True))
+        src_b = (k % self.pr) * self.pc + self.c
+        shape_b = (len(self.my_j), self.bs, self.bs)
+        buf_b = pb[k] if src_b == self.comm.rank else _empty_like_block(self.system, shape_b, self.like)
+        if self.pr > 1:
+            works.append(self.comm.broadcast(buf_b, src_b, self.col_groups[self.c], async_op=True))
+        a_panel = {i: buf_a[idx] for idx, i in enumerate(self.my_i)}
+        b_panel = {j: buf_b[idx] for idx, j in enumerate(self.my_j)}
         return a_panel, b_panel, [w for w in works if w is not None]
 
-    def run(self, a_blocks, b_blocks, flush_every=None):
+    def run(self, a_blocks, b_blocks=None, flush_every=1):
         """Returns {(i, j): block} for the C blocks this rank owns.
 
-        The local updates of `flush_every` consecutive k-steps (default: half the grid) are handed to
-        the system as one deferred chain, so they run as a single grouped GEMM launch that overlaps
-        with the broadcasts of the following steps and touches C only once per flush."""
+        `a_blocks` is either the result of ``pack`` or a dict of this rank's A blocks (then `b_blocks`
+        is the dict of B blocks and they are packed here).  The local updates of `flush_every`
+        consecutive k-steps are handed to the system as one deferred chain: one grouped GEMM launch
+        that overlaps with the broadcasts of the following step."""
+        packed = a_blocks if b_blocks is None else self.pack(a_blocks, b_blocks)
         shape = (self.bs, self.bs)
         c_blocks = {}
-        if flush_every is None:
-            flush_every = max(1, self.g // 2)
-        nxt = self._panels(0, a_blocks, b_blocks)
+        nxt = self._panels(0, packed)
         for k in range(self.g):
             a_panel, b_panel, works = nxt
             for w in works:
                 w.wait()
             if k + 1 < self.g:
-                nxt = self._panels(k + 1, a_blocks, b_blocks)   # prefetch while the GEMMs below run
+                nxt = self._panels(k + 1, packed)   # prefetch while the GEMMs below run
             for i in self.my_i:
                 for j in self.my_j:
                     sysk = {"grid_entry": (i, j), "grid_shape": (self.g, self.g)}
