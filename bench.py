@@ -414,7 +414,7 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=multi_gpu.nccl_options())
     comm = multi_gpu.Comm()
     system = CudaSystem(rank=rank, world_size=world)
     system.init()

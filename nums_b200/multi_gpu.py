@@ -32,6 +32,21 @@ def device_grid(world_size):
     return pr, world_size // pr
 
 
+def nccl_options():
+    """NCCL kernels on a HIGH-PRIORITY stream.  A long GEMM grid keeps thousands of CTAs pending; the
+    block scheduler only starts CTAs of a later, equal-priority kernel once those are all dispatched,
+    which would push every panel broadcast to the tail of the GEMM it is supposed to overlap with
+    (measured: 1.3 ms exposed per SUMMA step).  With priority the broadcast CTAs are picked as soon as
+    any GEMM tile retires."""
+    if not (dist.is_available() and dist.is_nccl_available() and torch.cuda.is_available()):
+        return None
+    if dist.is_initialized() and dist.get_backend() != "nccl":
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return opts
+
+
 class Comm(object):
     """Thin layer over ``torch.distributed`` that moves either torch tensors (NCCL, device memory)
     or NumPy arrays (gloo, used by the CPU tests)."""
@@ -48,7 +63,7 @@ class Comm(object):
         if len(ranks) == self.world:
             return None
         if ranks not in self._groups:
-            self._groups[ranks] = dist.new_group(list(ranks))
+            self._groups[ranks] = dist.new_group(list(ranks), pg_options=nccl_options())
         return self._groups[ranks]
 
     @staticmethod
