@@ -456,8 +456,10 @@ def run_gpu(args):
         packed = summa.pack(mine_a, mine_b)      # resident layout: one contiguous panel per k
         del mine_a, mine_b
 
+        flush_every = int(os.environ.get("NUMS_SUMMA_FLUSH", "2"))
+
         def step_resident():
-            return summa.run(packed)
+            return summa.run(packed, flush_every=flush_every)
 
         def step_e2e():
             la = {e: system.put(v) for e, v in a_host.items() if summa.owner_a(*e) == rank}

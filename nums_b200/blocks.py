@@ -176,8 +176,11 @@ class BlockArray(object):
         return cls(grid, system, blocks)
 
     def get(self):
-        out = np.zeros(self.shape, dtype=self.dtype)
         entries = list(self.grid.get_entry_iterator())
+        if len(entries) > 1 and hasattr(self.system, "get_assembled"):
+            # device-side assembly + one transfer (same result as the block-by-block path below)
+            return self.system.get_assembled(self.grid, [(e, self.blocks[e].oid) for e in entries])
+        out = np.zeros(self.shape, dtype=self.dtype)
         values = self.system.get([self.blocks[e].oid for e in entries])
         for entry, value in zip(entries, values):
             block = self.blocks[entry]

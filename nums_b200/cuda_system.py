@@ -94,6 +94,18 @@ class CudaSystem(object):
             return tuple(self.get(o) for o in object_ids)
         return cuda_compute.download(object_ids)
 
+    def get_assembled(self, grid, oids_by_entry):
+        """Whole array of a block grid as one NumPy array: the blocks are placed into a single device
+        buffer with the strided-copy kernel and come back in ONE page-locked D2H transfer, instead of
+        one transfer per block plus a host-side re-assembly (BlockArrayBase.get, base.py:348-360)."""
+        dtype = np.dtype(grid.dtype)
+        full = cuda_compute._empty(grid.shape, dtype)
+        for entry, oid in oids_by_entry:
+            block = self.contractions.resolve(oid)
+            view = full[grid.get_slice(entry)]
+            cuda_compute._copy_into(view, block.reshape(view.shape) if tuple(block.shape) != tuple(view.shape) else block)
+        return cuda_compute.download(full)
+
     def remote(self, function, remote_params):
         return function
 
