@@ -494,6 +494,20 @@ def run_gpu(args):
     seconds = float(elapsed.item())
     value = FLOPS_PER_STEP * args.steps / seconds / 1e12
 
+    if world > 1 and os.environ.get("NUMS_SUMMA_TRACE"):
+        summa.trace = []
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        step_resident()
+        step_resident()
+        torch.cuda.synchronize()
+        if rank == 0:
+            prev = t_start
+            for label, k, ev in summa.trace:
+                sys.stderr.write("TRACE %-13s k=%d  +%.3f ms  (t=%.3f)\n" % (label, k, prev.elapsed_time(ev), t_start.elapsed_time(ev)))
+                prev = ev
+        summa.trace = None
+
     # ---- timed: end to end (pinned host -> HBM -> kernels -> host) ------------------------------------------
     e2e_steps = max(1, min(args.steps, 3))
     step_e2e()

@@ -136,6 +136,7 @@ class SummaMatmul(object):
         self.col_groups = [comm.group([rr * self.pc + cc for rr in range(self.pr)]) for cc in range(self.pc)]
         self.my_i = [i for i in range(grid) if i % self.pr == self.r]
         self.my_j = [j for j in range(grid) if j % self.pc == self.c]
+        self.trace = None      # set to a list to record (label, k, cuda event) marks (development aid)
 
     def owner_a(self, i, k):
         return (i % self.pr) * self.pc + (k % self.pc)
@@ -190,11 +191,14 @@ class SummaMatmul(object):
         packed = a_blocks if b_blocks is None else self.pack(a_blocks, b_blocks)
         shape = (self.bs, self.bs)
         c_blocks = {}
+        trace = self.trace
         nxt = self._panels(0, packed)
         for k in range(self.g):
             a_panel, b_panel, works = nxt
             for w in works:
                 w.wait()
+            if trace is not None:
+                trace.append(("panels_ready", k, self._mark()))
             if k + 1 < self.g:
                 nxt = self._panels(k + 1, packed)   # prefetch while the GEMMs below run
             for i in self.my_i:
@@ -207,7 +211,14 @@ class SummaMatmul(object):
                         "add", prev, dot, shape, shape, False, False, axes=None, syskwargs=sysk)
             if hasattr(self.system, "flush") and ((k + 1) % flush_every == 0 or k + 1 == self.g):
                 self.system.flush()   # one grouped launch for the C += A(:,k) B(k,:) updates so far
+                if trace is not None:
+                    trace.append(("gemm_done", k, self._mark()))
         return c_blocks
+
+    def _mark(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
 
 
 # ---------------------------------------------------------------------------------------------
