@@ -401,6 +401,92 @@ def sharded_workloads(system, comm, quick):
     return out
 
 
+def run_large(args):
+    """BASELINE.json configs[4]: float64 65536 x 65536 @ 65536 x 65536, 8 x 8 grid of 8192 x 8192 blocks
+    (34.4 GB per operand, 103 GB resident).  Blocks are generated on the device, block by block (seeded);
+    parity is checked on a sampled 512 x 512 corner of one C block against NumPy on the host."""
+    import torch
+    import torch.distributed as dist
+    from nums_b200 import _lib, multi_gpu
+    from nums_b200.cuda_system import CudaSystem
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=multi_gpu.nccl_options())
+    comm = multi_gpu.Comm()
+    system = CudaSystem(rank=rank, world_size=world)
+    system.init()
+    n, bs, g = 65536, 8192, 8
+    dev = torch.device("cuda", local_rank)
+
+    def block(seed, i, j):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed * 1000 + i * 8 + j)
+        return torch.randn((bs, bs), dtype=torch.float64, device=dev, generator=gen)
+    like = torch.empty((1,), dtype=torch.float64, device=dev)
+    summa = multi_gpu.SummaMatmul(system, comm, g, bs, like)
+    # fill the packed per-k panels directly (no second copy of the operands: 103 GB must fit one GPU)
+    pa, pb = {}, {}
+    for k in range(g):
+        if k % summa.pc == summa.c:
+            pa[k] = torch.empty((len(summa.my_i), bs, bs), dtype=torch.float64, device=dev)
+            for idx, i in enumerate(summa.my_i):
+                pa[k][idx].copy_(block(3, i, k))
+        if k % summa.pr == summa.r:
+            pb[k] = torch.empty((len(summa.my_j), bs, bs), dtype=torch.float64, device=dev)
+            for idx, j in enumerate(summa.my_j):
+                pb[k][idx].copy_(block(4, k, j))
+    packed = (pa, pb)
+    torch.cuda.empty_cache()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        comm.barrier()
+        torch.cuda.synchronize()
+    c = None
+    for _ in range(max(1, args.warmup)):
+        c = None
+        c = summa.run(packed)
+    sync_all()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        c = None                   # release the previous result before the next one is allocated
+        c = summa.run(packed)
+    end.record()
+    end.synchronize()
+    sync_all()
+    elapsed = torch.tensor([start.elapsed_time(end) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    seconds = float(elapsed.item())
+    flops = 2.0 * n ** 3
+    rel = None
+    if rank == 0:
+        (i, j) = sorted(c)[0]
+        got = system.get(system.contractions.resolve(c[(i, j)])[:512, :512])
+        ref = np.zeros((512, 512))
+        for k in range(g):
+            a = block(3, i, k)[:512].cpu().numpy()
+            bcol = block(4, k, j)[:, :512].contiguous().cpu().numpy()
+            ref += a @ bcol
+        rel = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        line = {"metric": "blocked_matmul_fp64_tflops", "value": flops * args.steps / seconds / 1e12, "unit": "TFLOP/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
+                "ms_per_step": seconds / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "blocked matmul float64 65536x65536 @ 65536x65536, 8x8 grid of 8192x8192 blocks "
+                                       "(BASELINE.json configs[4]), SUMMA on a %dx%d device grid" % multi_gpu.device_grid(world)},
+                "parity_check": {"what": "512x512 corner of one C block vs NumPy on the host", "rel_err": rel, "bar": 1e-10},
+                "resident_gb_per_gpu": torch.cuda.max_memory_allocated() / 1e9}
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -456,7 +542,7 @@ def run_gpu(args):
         packed = summa.pack(mine_a, mine_b)      # resident layout: one contiguous panel per k
         del mine_a, mine_b
 
-        flush_every = int(os.environ.get("NUMS_SUMMA_FLUSH", "2"))
+        flush_every = int(os.environ.get("NUMS_SUMMA_FLUSH", "1"))
 
         def step_resident():
             return summa.run(packed, flush_every=flush_every)
@@ -649,9 +735,12 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-workloads", action="store_true", help="only the headline matmul")
     ap.add_argument("--quick", action="store_true", help="fewer repetitions of the secondary workloads")
+    ap.add_argument("--large", action="store_true", help="config 5 instead: 65536^2 matmul (one-off record run)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.large:
+        run_large(args)
     else:
         run_gpu(args)
 
