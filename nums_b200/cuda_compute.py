@@ -688,6 +688,21 @@ def _householder_r(arr):
     return r
 
 
+def sum_of_squares(t):
+    """sum(t * t) as a 0-d device tensor (multiply + two-stage sum, both ours)."""
+    if not t.is_contiguous():
+        t = _materialize(t)
+    n = t.numel()
+    flat = t.view(n)
+    sq = _empty((n,), _lib.numpy_dtype(t.dtype))
+    code = _lib.dtype_code(t.dtype)
+    LIB.check(LIB.dll.nums_bop(_lib.BOP_CODE["multiply"], code, describe(flat), describe(flat), describe(sq), _stream()))
+    out = _empty((), _lib.numpy_dtype(t.dtype))
+    LIB.call_ws(LIB.dll.nums_reduce, t.device,
+                ((_lib.REDUCE_CODE["sum"], sq.data_ptr(), code, 1, n, 1, out.data_ptr(), code), (_stream(),)))
+    return out
+
+
 def _norm_1_inf(t):
     """(max column abs-sum, max row abs-sum) of a square matrix, as two 0-d device tensors."""
     n = t.shape[0]

@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the tests exercise the built artefact: (re)build libnumscuda.so if it is missing (nvcc needed)
+    from nums_b200 import _build
+    if not os.path.exists(_build.LIB):
+        _build.build()
 
 
 def pytest_collection_modifyitems(config, items):
