@@ -12,6 +12,8 @@
 //     HBM-bound streaming kernels.
 //   * everything else (f32, exact integer tensordot from tests/core/array/test_bop.py:38-42,
 //     unaligned f64): a plain shared-memory tiled kernel.
+#include <cuda.h>   // CUtensorMap types; the encoder itself is fetched through cudaGetDriverEntryPoint
+#include <cstdlib>
 #include <vector>
 #include "common.cuh"
 
@@ -323,6 +325,238 @@ dgemm_dmma_kernel(GemmParams p) {
   cp_async_wait<0>();
 
   // Epilogue: lane (g, t) owns C[m = 8i + g][n = 8j + 2t, 2t + 1].
+  double* out = prob.C + (int64_t)blockIdx.z * p.split_stride;
+  const bool vec_ok = (prob.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + wm + i * 8 + g;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t n = n0 + wn + j * 8 + 2 * t;
+      if (n >= N) continue;
+      double* dst = out + m * prob.ldc + n;
+      if (n + 1 < N) {
+        if (vec_ok) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+        else {
+          dst[0] = acc[i][j][0];
+          dst[1] = acc[i][j][1];
+        }
+      } else {
+        dst[0] = acc[i][j][0];
+      }
+    }
+  }
+}
+
+// ======================================================================================
+// TMA-fed, warp-specialised variant of the same tile kernel
+// ======================================================================================
+// Same tiles, fragments and shared-memory layout as dgemm_dmma_kernel, but the ring is filled by
+// the TMA engine from 2-D tensor maps: a ninth (producer) warp issues TWO
+// cp.async.bulk.tensor.2d copies per k-tile (UTMALDG), one per operand.  The box of each map is
+// (tile rows) x (tile columns + 4): the four extra columns are fetched and never read, which makes
+// the dense box land exactly at the padded pitch (== 4 mod 16 doubles) the conflict-free fragment
+// reads need -- no swizzle, no per-row copies (a first version issued one bulk copy per tile row and
+// was limited by the ~60-cycle issue rate of the copy engine whenever rows were 256 bytes).  The
+// engine zero-fills everything outside the tensor, so ragged M / N / K edges need no special code.
+// `full` mbarriers (transaction bytes) hand stages to the eight MMA warps, `empty` mbarriers hand
+// them back; there is no CTA-wide barrier in the main loop and no copy instruction in the MMA warps.
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}\n" ::"r"(smem_addr_u32(bar)), "r"(parity) : "memory");
+}
+// One box of a 2-D tensor map -> shared memory; c0 = column (innermost) index, c1 = row index.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+          smem_addr_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_addr_u32(bar))
+      : "memory");
+}
+
+constexpr int kTmaThreads = kGemmThreads + 32;
+
+// Tensor maps of one contraction term (operand A, operand B) and its K.
+struct alignas(64) TmaTerm {
+  CUtensorMap a;
+  CUtensorMap b;
+  int64_t K;
+  int64_t pad_[7];
+};
+static_assert(sizeof(TmaTerm) % 64 == 0, "tensor maps must stay 64-byte aligned in the table");
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+dgemm_dmma_tma_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TmaTerm single_tma,
+                      const TmaTerm* __restrict__ tma_terms) {
+  extern __shared__ __align__(128) double smem[];
+  using AT = ATile<TA>;
+  using BT = BTile<TB>;
+  double* sA = smem;
+  double* sB = smem + kStages * AT::doubles;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + kStages * BT::doubles);
+  uint64_t* empty = full + kStages;
+  constexpr uint32_t kStageBytes = (uint32_t)((AT::doubles + BT::doubles) * sizeof(double));
+
+  GemmProblem prob;
+  if (p.use_table) {
+    int lo = 0, hi = p.nproblems - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (p.problems[mid].tile_begin <= (int)blockIdx.x) lo = mid;
+      else hi = mid - 1;
+    }
+    prob = p.problems[lo];
+  } else {
+    prob = p.single;
+  }
+  const int tile = (int)blockIdx.x - prob.tile_begin;
+  constexpr int kGroup = 8;
+  const int tiles_per_group = kGroup * prob.tiles_n;
+  const int group = tile / tiles_per_group;
+  const int first_m = group * kGroup;
+  const int group_rows = min(prob.tiles_m - first_m, kGroup);
+  const int tm = first_m + (tile % tiles_per_group) % group_rows;
+  const int tn = (tile % tiles_per_group) / group_rows;
+  const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+  const int64_t M = prob.M, N = prob.N;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kGemmThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  const TmaTerm* first_term = p.use_table ? tma_terms + prob.term_begin : &single_tma;
+  int64_t k_lo = 0, k_hi = first_term->K;
+  if (p.k_per_split > 0) {   // split-K slice of a single-term problem (k_per_split is a multiple of BK)
+    k_lo = (int64_t)blockIdx.z * p.k_per_split;
+    k_hi = k_lo + p.k_per_split;
+    if (k_hi > first_term->K) k_hi = first_term->K;
+  }
+  int KT = 0;
+  if (p.use_table) {
+    for (int s = 0; s < prob.term_count; ++s) KT += (int)((tma_terms[prob.term_begin + s].K + BK - 1) / BK);
+  } else {
+    KT = (int)((k_hi - k_lo + BK - 1) / BK);
+  }
+
+  if (warp == kGemmThreads / 32) {
+    // ===== producer warp: one elected lane drives the copy engine =====
+    if (lane == 0) {
+      const TmaTerm* term = first_term;
+      int term_idx = 0;
+      int k_cur = (int)k_lo;
+      int64_t k_end = k_hi;
+      for (int kt = 0; kt < KT; ++kt) {
+        const int slot = kt % kStages;
+        const int round = kt / kStages;
+        if (round > 0) {
+          mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before async writes
+        }
+        mbar_expect_tx(&full[slot], kStageBytes);
+        // A: "N" storage (m, k) -> box origin (col k, row m).  "T" storage (k, m) -> (col m, row k).
+        tma_load_2d(sA + slot * AT::doubles, &term->a, TA ? (int)m0 : k_cur, TA ? k_cur : (int)m0, &full[slot]);
+        // B: "N" storage (k, n) -> (col n, row k).  "T" storage (n, k) -> (col k, row n).
+        tma_load_2d(sB + slot * BT::doubles, &term->b, TB ? k_cur : (int)n0, TB ? (int)n0 : k_cur, &full[slot]);
+        k_cur += BK;
+        if (k_cur >= k_end && term_idx + 1 < prob.term_count) {
+          ++term_idx;
+          ++term;
+          k_cur = 0;
+          k_end = term->K;
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== MMA warps =====
+  const int wm = (warp & 3) * 32;
+  const int wn = (warp >> 2) * 64;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][8][2];
+  if (prob.Cin != nullptr && blockIdx.z == 0) {
+    const bool cin_vec = (prob.ldcin % 2 == 0) && ((reinterpret_cast<uintptr_t>(prob.Cin) & 15u) == 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + wm + i * 8 + g;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t n = n0 + wn + j * 8 + 2 * t;
+        double v0 = 0.0, v1 = 0.0;
+        if (m < M && n < N) {
+          const double* src = prob.Cin + m * prob.ldcin + n;
+          if (n + 1 < N && cin_vec) {
+            const double2 v = *reinterpret_cast<const double2*>(src);
+            v0 = v.x;
+            v1 = v.y;
+          } else {
+            v0 = src[0];
+            if (n + 1 < N) v1 = src[1];
+          }
+        }
+        acc[i][j][0] = v0;
+        acc[i][j][1] = v1;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    const int slot = kt % kStages;
+    mbar_wait(&full[slot], (uint32_t)((kt / kStages) & 1));
+    const double* a = sA + slot * AT::doubles;
+    const double* b = sB + slot * BT::doubles;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[4], bf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = wm + i * 8 + g, k = kk + t;
+        af[i] = TA ? a[k * AT::pitch + m] : a[m * AT::pitch + k];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = wn + j * 8 + g, k = kk + t;
+        bf[j] = TB ? b[n * BT::pitch + k] : b[k * BT::pitch + n];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma884(acc[i][j], af[i], bf[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
+  }
+
   double* out = prob.C + (int64_t)blockIdx.z * p.split_stride;
   const bool vec_ok = (prob.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
 #pragma unroll
@@ -807,6 +1041,67 @@ int run_dot(const T* x, int64_t incx, const T* y, int64_t incy, int64_t n, const
   return NUMS_OK;
 }
 
+// ---- tensor maps -------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the library does not link
+// libcuda).  NUMS_GEMM_FEED=cpasync forces the LDGSTS ring for A/B comparisons.
+EncodeTiledFn tensor_map_encoder() {
+  static const EncodeTiledFn fn = []() -> EncodeTiledFn {
+    const char* v = getenv("NUMS_GEMM_FEED");
+    if (v && strcmp(v, "cpasync") == 0) return nullptr;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// Map of a row-major (rows x cols) float64 matrix with pitch ld, fetched in (box_rows x box_cols) boxes.
+bool encode_matrix_map(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                       int box_cols) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || rows < 1 || cols < 1 || rows >= (1LL << 31) || cols >= (1LL << 31)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t elem[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, elem,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Maps of one term: op(A) is M x K, op(B) is K x N; boxes are the padded shared-memory tiles.
+bool encode_term(TmaTerm* out, int ta, int tb, int64_t M, int64_t N, const GemmTerm& t) {
+  memset(out, 0, sizeof(*out));
+  out->K = t.K;
+  const bool a_ok = ta ? encode_matrix_map(&out->a, t.A, t.K, M, t.lda, ATile<true>::rows, ATile<true>::pitch)
+                       : encode_matrix_map(&out->a, t.A, M, t.K, t.lda, ATile<false>::rows, ATile<false>::pitch);
+  if (!a_ok) return false;
+  return tb ? encode_matrix_map(&out->b, t.B, N, t.K, t.ldb, BTile<true>::rows, BTile<true>::pitch)
+            : encode_matrix_map(&out->b, t.B, t.K, N, t.ldb, BTile<false>::rows, BTile<false>::pitch);
+}
+
+template <bool TA, bool TB>
+int launch_dmma_tma(const GemmParams& p, const TmaTerm& single, const TmaTerm* table, unsigned tiles, int splits,
+                    cudaStream_t s) {
+  const size_t smem = (size_t)kStages * (ATile<TA>::doubles + BTile<TB>::doubles) * sizeof(double) +
+                      2 * kStages * sizeof(uint64_t);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_tma_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  dim3 grid(tiles, 1, (unsigned)splits);
+  dgemm_dmma_tma_kernel<TA, TB><<<grid, kTmaThreads, smem, s>>>(p, single, table);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
 template <bool TA, bool TB>
 int launch_dmma(const GemmParams& p, unsigned tiles, int splits, cudaStream_t s) {
   const size_t smem = (size_t)kStages * (ATile<TA>::doubles + BTile<TB>::doubles) * sizeof(double);
@@ -818,7 +1113,18 @@ int launch_dmma(const GemmParams& p, unsigned tiles, int splits, cudaStream_t s)
   return NUMS_OK;
 }
 
-int dispatch_dmma(int ta, int tb, const GemmParams& p, unsigned tiles, int splits, cudaStream_t s) {
+// `single` (one term, maps passed as kernel parameters) or `table` (device array, one entry per term)
+// select the TMA-fed kernel; with neither, the cp.async ring runs.
+int dispatch_dmma(int ta, int tb, const GemmParams& p, unsigned tiles, int splits, cudaStream_t s,
+                  const TmaTerm* single = nullptr, const TmaTerm* table = nullptr) {
+  if (single || table) {
+    static const TmaTerm none = {};
+    const TmaTerm& one = single ? *single : none;
+    if (ta && tb) return launch_dmma_tma<true, true>(p, one, table, tiles, splits, s);
+    if (ta) return launch_dmma_tma<true, false>(p, one, table, tiles, splits, s);
+    if (tb) return launch_dmma_tma<false, true>(p, one, table, tiles, splits, s);
+    return launch_dmma_tma<false, false>(p, one, table, tiles, splits, s);
+  }
   if (ta && tb) return launch_dmma<true, true>(p, tiles, splits, s);
   if (ta) return launch_dmma<true, false>(p, tiles, splits, s);
   if (tb) return launch_dmma<false, true>(p, tiles, splits, s);
@@ -865,7 +1171,9 @@ int run_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, const double* A, 
   } else {
     p.k_per_split = 0;
   }
-  if (int rc = dispatch_dmma(ta, tb, p, (unsigned)tiles, splits, s)) return rc;
+  TmaTerm maps;
+  const bool tma_ok = encode_term(&maps, ta, tb, M, N, p.single_term);
+  if (int rc = dispatch_dmma(ta, tb, p, (unsigned)tiles, splits, s, tma_ok ? &maps : nullptr)) return rc;
   if (splits > 1) {
     splitk_fold_kernel<<<blocks_for(M * N, 256, (int64_t)sms * 8), 256, 0, s>>>(
         static_cast<const double*>(ws), splits, M, N, Cin, ldcin, C, ldc);
@@ -962,8 +1270,7 @@ extern "C" int nums_gemm_grouped(int dtype, int trans_a, int trans_b, int nprobl
   NUMS_REQUIRE(nproblems >= 1 && nterms >= nproblems && problems_host && terms_host, "gemm_grouped: empty group");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t prob_bytes = ((size_t)nproblems * sizeof(GemmProblem) + 255) & ~(size_t)255;
-  const size_t term_bytes = (size_t)nterms * sizeof(GemmTerm);
-  NUMS_NEED_WS(prob_bytes + term_bytes, ws_bytes);
+  const size_t term_bytes = ((size_t)nterms * sizeof(GemmTerm) + 255) & ~(size_t)255;
   std::vector<GemmProblem> probs((size_t)nproblems);
   std::vector<GemmTerm> terms((size_t)nterms);
   int64_t tile_cursor = 0;
@@ -994,15 +1301,32 @@ extern "C" int nums_gemm_grouped(int dtype, int trans_a, int trans_b, int nprobl
     d.B = static_cast<const double*>(src.B);
     d.lda = src.lda; d.ldb = src.ldb; d.K = src.k;
   }
+  // tensor maps, one pair per term (the TMA-fed kernel); any failure selects the cp.async ring
+  std::vector<TmaTerm> maps;
+  bool tma_ok = tensor_map_encoder() != nullptr;
+  if (tma_ok) {
+    maps.resize((size_t)nterms);
+    for (int i = 0; i < nproblems && tma_ok; ++i) {
+      const GemmProblem& d = probs[(size_t)i];
+      for (int t = d.term_begin; t < d.term_begin + d.term_count && tma_ok; ++t)
+        tma_ok = encode_term(&maps[(size_t)t], trans_a, trans_b, d.M, d.N, terms[(size_t)t]);
+    }
+  }
+  const size_t map_bytes = tma_ok ? (size_t)nterms * sizeof(TmaTerm) : 0;
+  NUMS_NEED_WS(prob_bytes + term_bytes + map_bytes, ws_bytes);
   char* base = static_cast<char*>(ws);
+  NUMS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 63u) == 0, "gemm_grouped: workspace must be 64-byte aligned");
   // pageable sources: the runtime stages them before returning, so the vectors may die here
   NUMS_CUDA_OK(cudaMemcpyAsync(base, probs.data(), (size_t)nproblems * sizeof(GemmProblem), cudaMemcpyHostToDevice, s));
-  NUMS_CUDA_OK(cudaMemcpyAsync(base + prob_bytes, terms.data(), term_bytes, cudaMemcpyHostToDevice, s));
+  NUMS_CUDA_OK(cudaMemcpyAsync(base + prob_bytes, terms.data(), (size_t)nterms * sizeof(GemmTerm), cudaMemcpyHostToDevice, s));
+  if (tma_ok)
+    NUMS_CUDA_OK(cudaMemcpyAsync(base + prob_bytes + term_bytes, maps.data(), map_bytes, cudaMemcpyHostToDevice, s));
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.problems = reinterpret_cast<const GemmProblem*>(base);
   p.terms = reinterpret_cast<const GemmTerm*>(base + prob_bytes);
   p.nproblems = nproblems;
   p.use_table = 1;
-  return dispatch_dmma(trans_a, trans_b, p, (unsigned)tile_cursor, 1, s);
+  return dispatch_dmma(trans_a, trans_b, p, (unsigned)tile_cursor, 1, s, nullptr,
+                       tma_ok ? reinterpret_cast<const TmaTerm*>(base + prob_bytes + term_bytes) : nullptr);
 }
