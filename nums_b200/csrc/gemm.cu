@@ -14,6 +14,7 @@
 //     unaligned f64): a plain shared-memory tiled kernel.
 #include <cuda.h>   // CUtensorMap types; the encoder itself is fetched through cudaGetDriverEntryPoint
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 #include "common.cuh"
 
@@ -403,6 +404,26 @@ struct alignas(64) TmaTerm {
 };
 static_assert(sizeof(TmaTerm) % 64 == 0, "tensor maps must stay 64-byte aligned in the table");
 
+// The term table is written by table_copy_kernel (generic proxy) in an earlier launch on the same
+// stream; the copy engine reads descriptors through the tensormap proxy, so the reader acquires
+// each pair of maps before its first use (the writer releases, see table_copy_kernel).
+__device__ __forceinline__ void tensormap_acquire(const TmaTerm* term) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;\n" ::"l"(reinterpret_cast<uint64_t>(&term->a)) : "memory");
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;\n" ::"l"(reinterpret_cast<uint64_t>(&term->b)) : "memory");
+}
+
+// Descriptor tables: page-locked host staging (mapped into the device address space) -> workspace.
+// A kernel rather than cudaMemcpyAsync, because a host-to-device copy queues on the copy engine
+// BEHIND every block upload already submitted on other streams (measured: the first launch group of
+// a pipelined matmul started only after all 4 GiB of operands had landed), while a kernel only
+// waits for its own stream.
+__global__ void __launch_bounds__(256)
+table_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t count) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+  asm volatile("fence.proxy.tensormap::generic.release.gpu;\n" ::: "memory");
+}
+
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 dgemm_dmma_tma_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TmaTerm single_tma,
@@ -468,6 +489,7 @@ dgemm_dmma_tma_kernel(const __grid_constant__ GemmParams p, const __grid_constan
     if (lane == 0) {
       const TmaTerm* term = first_term;
       int term_idx = 0;
+      if (p.use_table) tensormap_acquire(term);
       int k_cur = (int)k_lo;
       int64_t k_end = k_hi;
       for (int kt = 0; kt < KT; ++kt) {
@@ -486,6 +508,7 @@ dgemm_dmma_tma_kernel(const __grid_constant__ GemmParams p, const __grid_constan
         if (k_cur >= k_end && term_idx + 1 < prob.term_count) {
           ++term_idx;
           ++term;
+          tensormap_acquire(term);
           k_cur = 0;
           k_end = term->K;
         }
@@ -1131,6 +1154,63 @@ int dispatch_dmma(int ta, int tb, const GemmParams& p, unsigned tiles, int split
   return launch_dmma<false, false>(p, tiles, splits, s);
 }
 
+// Page-locked staging for the descriptor tables of a grouped launch.  cudaMemcpyAsync from pageable
+// memory synchronises the stream before it copies, which would block the host behind every queued
+// GEMM (and with it the issue of the next SUMMA broadcasts); from page-locked memory it is an
+// ordinary asynchronous copy.  A small ring of slots, each guarded by an event recorded after its
+// copy, keeps the host from overwriting tables that have not been transferred yet.
+class TableStaging {
+ public:
+  static constexpr int kSlots = 8;
+  // Locks the ring; returns a pinned buffer of at least `bytes` (nullptr: use pageable memory).
+  char* acquire(size_t bytes) {
+    mu_.lock();
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    Slot& sl = slots_[dev][next_[dev]];
+    current_ = &sl;
+    next_[dev] = (next_[dev] + 1) % kSlots;
+    if (sl.event && cudaEventSynchronize(sl.event) != cudaSuccess) { (void)cudaGetLastError(); current_ = nullptr; return nullptr; }
+    if (sl.cap < bytes) {
+      if (sl.ptr) cudaFreeHost(sl.ptr);
+      sl.ptr = nullptr;
+      sl.cap = 0;
+      const size_t want = bytes < (size_t)(64 << 10) ? (size_t)(64 << 10) : bytes + bytes / 2;
+      if (cudaHostAlloc(reinterpret_cast<void**>(&sl.ptr), want, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        (void)cudaGetLastError();
+        sl.ptr = nullptr;
+        current_ = nullptr;
+        return nullptr;
+      }
+      sl.cap = want;
+    }
+    return sl.ptr;
+  }
+  // Marks the slot busy until everything queued on `s` so far has run, and unlocks the ring.
+  void release(cudaStream_t s) {
+    if (current_) {
+      if (!current_->event && cudaEventCreateWithFlags(&current_->event, cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();
+        current_->event = nullptr;
+        cudaStreamSynchronize(s);   // no event: fall back to a hard wait so the slot is free again
+      } else {
+        cudaEventRecord(current_->event, s);
+      }
+    }
+    current_ = nullptr;
+    mu_.unlock();
+  }
+
+ private:
+  static constexpr int kMaxDevices = 16;
+  struct Slot { char* ptr = nullptr; size_t cap = 0; cudaEvent_t event = nullptr; };
+  Slot slots_[kMaxDevices][kSlots];
+  int next_[kMaxDevices] = {};
+  Slot* current_ = nullptr;
+  std::mutex mu_;
+};
+TableStaging g_table_staging;
+
 int run_dgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
               int64_t ldb, const double* Cin, int64_t ldcin, double* C, int64_t ldc, void* ws,
               size_t ws_bytes, cudaStream_t s) {
@@ -1313,14 +1393,35 @@ extern "C" int nums_gemm_grouped(int dtype, int trans_a, int trans_b, int nprobl
     }
   }
   const size_t map_bytes = tma_ok ? (size_t)nterms * sizeof(TmaTerm) : 0;
-  NUMS_NEED_WS(prob_bytes + term_bytes + map_bytes, ws_bytes);
+  const size_t total_bytes = prob_bytes + term_bytes + map_bytes;
+  NUMS_NEED_WS(total_bytes, ws_bytes);
   char* base = static_cast<char*>(ws);
   NUMS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 63u) == 0, "gemm_grouped: workspace must be 64-byte aligned");
-  // pageable sources: the runtime stages them before returning, so the vectors may die here
-  NUMS_CUDA_OK(cudaMemcpyAsync(base, probs.data(), (size_t)nproblems * sizeof(GemmProblem), cudaMemcpyHostToDevice, s));
-  NUMS_CUDA_OK(cudaMemcpyAsync(base + prob_bytes, terms.data(), (size_t)nterms * sizeof(GemmTerm), cudaMemcpyHostToDevice, s));
-  if (tma_ok)
-    NUMS_CUDA_OK(cudaMemcpyAsync(base + prob_bytes + term_bytes, maps.data(), map_bytes, cudaMemcpyHostToDevice, s));
+  // one table image [problems | terms | maps] -> one copy, from page-locked staging when available
+  char* stage = g_table_staging.acquire(total_bytes);
+  std::vector<char> pageable;
+  char* image = stage;
+  if (!image) {
+    pageable.resize(total_bytes);
+    image = pageable.data();
+  }
+  memcpy(image, probs.data(), (size_t)nproblems * sizeof(GemmProblem));
+  memcpy(image + prob_bytes, terms.data(), (size_t)nterms * sizeof(GemmTerm));
+  if (tma_ok) memcpy(image + prob_bytes + term_bytes, maps.data(), map_bytes);
+  cudaError_t copy_err = cudaSuccess;
+  void* mapped = nullptr;
+  if (stage && cudaHostGetDevicePointer(&mapped, stage, 0) == cudaSuccess && mapped) {
+    const size_t count = total_bytes / sizeof(uint4);   // every section is a multiple of 16 bytes
+    table_copy_kernel<<<(unsigned)((count + 255) / 256 < 64 ? (count + 255) / 256 : 64), 256, 0, s>>>(
+        static_cast<const uint4*>(mapped), reinterpret_cast<uint4*>(base), count);
+    copy_err = cudaGetLastError();
+    count_launch();
+  } else {
+    (void)cudaGetLastError();
+    copy_err = cudaMemcpyAsync(base, image, total_bytes, cudaMemcpyHostToDevice, s);
+  }
+  g_table_staging.release(s);
+  NUMS_CUDA_OK(copy_err);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.problems = reinterpret_cast<const GemmProblem*>(base);

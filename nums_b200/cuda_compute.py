@@ -76,8 +76,59 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _stream():
+class _Transfers(object):
+    """Copy streams of the host<->HBM pipeline.
+
+    ``upload`` of a large page-locked array runs on ``up`` and returns at once; the tensor carries
+    ``_nums_ready = (sequence number, event)``.  Every kernel launch fetches its stream through
+    ``_stream()``, which first makes that stream wait for *all* uploads issued so far -- except the
+    deferred-contraction flush (deferred.py), which waits per launch group only for the operands the
+    group reads, so the grouped GEMM starts while later blocks are still crossing PCIe.  ``down`` is
+    used by ``CudaSystem.get_assembled`` to drain finished block rows while later rows compute.
+    """
+    up = None
+    down = None
+    seq = 0            # sequence number of the latest upload
+    last_event = None
+    awaited = {}       # stream handle -> highest sequence number that stream has waited for
+
+
+def _upload_stream():
+    if _Transfers.up is None:
+        _Transfers.up = torch.cuda.Stream()
+    return _Transfers.up
+
+
+def _download_stream():
+    if _Transfers.down is None:
+        _Transfers.down = torch.cuda.Stream()
+    return _Transfers.down
+
+
+def await_uploads(stream=None, upto=None):
+    """Order ``stream`` (default: current) after the uploads up to ``upto`` = (sequence number, event)
+    (default: every upload issued so far)."""
+    if _Transfers.last_event is None:
+        return
+    cur = torch.cuda.current_stream() if stream is None else stream
+    key = cur.cuda_stream
+    seq, event = (_Transfers.seq, _Transfers.last_event) if upto is None else upto
+    if _Transfers.awaited.get(key, 0) < seq:
+        cur.wait_event(event)
+        _Transfers.awaited[key] = seq
+
+
+def _stream_unordered():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _stream():
+    cur = torch.cuda.current_stream()
+    key = cur.cuda_stream
+    if _Transfers.seq and _Transfers.awaited.get(key, 0) < _Transfers.seq:
+        cur.wait_event(_Transfers.last_event)
+        _Transfers.awaited[key] = _Transfers.seq
+    return key
 
 
 def _empty(shape, dtype):
@@ -87,8 +138,9 @@ def _empty(shape, dtype):
 def upload(value, dtype=None):
     """Host value -> device tensor on the current stream.
 
-    Page-locked sources (e.g. arrays backed by ``torch.empty(pin_memory=True)``) are copied
-    asynchronously straight from where they are; pageable ones go through the driver's own staging.
+    Large page-locked sources (e.g. arrays backed by ``torch.empty(pin_memory=True)``) are copied
+    asynchronously on the upload stream straight from where they are (see ``_Transfers``); pageable
+    ones go through the driver's own staging on the current stream.
     """
     if isinstance(value, torch.Tensor):
         return value
@@ -102,8 +154,21 @@ def upload(value, dtype=None):
     if not arr.flags.writeable:
         arr = arr.copy()
     host = torch.from_numpy(arr)
-    big = host.numel() * host.element_size() >= (1 << 20)
-    return host.to(_device(), non_blocking=bool(big and host.is_pinned()))
+    if host.numel() * host.element_size() >= (1 << 20) and host.is_pinned():
+        # asynchronous, on the upload stream; consumers order themselves through _stream()
+        device = _device()
+        home = torch.cuda.current_stream()
+        with torch.cuda.stream(_upload_stream()):
+            dev = torch.empty(host.shape, dtype=host.dtype, device=device)
+            dev.copy_(host, non_blocking=True)
+        dev.record_stream(home)
+        event = torch.cuda.Event()
+        event.record(_Transfers.up)
+        _Transfers.seq += 1
+        _Transfers.last_event = event
+        dev._nums_ready = (_Transfers.seq, event)
+        return dev
+    return host.to(_device())
 
 
 def _to_pinned(t):
@@ -111,6 +176,7 @@ def _to_pinned(t):
     recycles the buffers, so steady-state loops do not pay cudaHostAlloc)."""
     if not t.is_contiguous():
         t = _materialize(t)
+    await_uploads()
     host = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
     host.copy_(t, non_blocking=True)
     return host
@@ -126,6 +192,7 @@ def download(t):
     if t.numel() * t.element_size() < (1 << 16):
         if not t.is_contiguous():
             t = _materialize(t)
+        await_uploads()
         return t.cpu().numpy()
     host = _to_pinned(t)
     torch.cuda.current_stream().synchronize()

@@ -95,16 +95,54 @@ class CudaSystem(object):
         return cuda_compute.download(object_ids)
 
     def get_assembled(self, grid, oids_by_entry):
-        """Whole array of a block grid as one NumPy array: the blocks are placed into a single device
-        buffer with the strided-copy kernel and come back in ONE page-locked D2H transfer, instead of
-        one transfer per block plus a host-side re-assembly (BlockArrayBase.get, base.py:348-360)."""
+        """Whole array of a block grid as one NumPy array (BlockArrayBase.get, base.py:348-360).
+
+        The blocks are placed into one device buffer with the strided-copy kernel and come back as
+        page-locked D2H transfers of whole block rows (contiguous in the C-ordered result) instead of
+        one transfer per block plus a host-side re-assembly.  Assembly and transfers run on the
+        download stream, each block row as soon as the launch group that produced its blocks has
+        finished (``_nums_done`` events set by the deferred-contraction flush), so the D2H of early
+        rows overlaps the GEMM of later ones."""
+        cc = cuda_compute
         dtype = np.dtype(grid.dtype)
-        full = cuda_compute._empty(grid.shape, dtype)
-        for entry, oid in oids_by_entry:
-            block = self.contractions.resolve(oid)
-            view = full[grid.get_slice(entry)]
-            cuda_compute._copy_into(view, block.reshape(view.shape) if tuple(block.shape) != tuple(view.shape) else block)
-        return cuda_compute.download(full)
+        tdtype = cuda_compute._lib.torch_dtype(dtype)
+        shape = tuple(int(x) for x in grid.shape)
+        if len(shape) == 0 or int(np.prod(shape)) * dtype.itemsize < (1 << 20):
+            full = cc._empty(shape, dtype)
+            for entry, oid in oids_by_entry:
+                block = self.contractions.resolve(oid)
+                view = full[grid.get_slice(entry)]
+                cc._copy_into(view, block.reshape(view.shape) if tuple(block.shape) != tuple(view.shape) else block)
+            return cc.download(full)
+        blocks = [(entry, self.contractions.resolve(oid)) for entry, oid in oids_by_entry]
+        home = torch.cuda.current_stream()
+        cc.await_uploads(home)
+        tail = None                      # producers without their own event: everything queued so far
+        down = cc._download_stream()
+        host = torch.empty(shape, dtype=tdtype, pin_memory=True)
+        rows = {}
+        for entry, block in blocks:
+            rows.setdefault(entry[0], []).append((entry, block))
+        with torch.cuda.stream(down):
+            full = torch.empty(shape, dtype=tdtype, device=cc._device())
+            for r in sorted(rows):
+                lo = hi = None
+                for entry, block in rows[r]:
+                    done = getattr(block, "_nums_done", None)
+                    if done is None:
+                        if tail is None:
+                            tail = torch.cuda.Event()
+                            tail.record(home)
+                        done = tail
+                    down.wait_event(done)
+                    block.record_stream(down)
+                    sl = grid.get_slice(entry)
+                    view = full[sl]
+                    cc._copy_into(view, block.reshape(view.shape) if tuple(block.shape) != tuple(view.shape) else block)
+                    lo, hi = sl[0].start, sl[0].stop
+                host[lo:hi].copy_(full[lo:hi], non_blocking=True)
+        down.synchronize()
+        return host.numpy()
 
     def remote(self, function, remote_params):
         return function

@@ -20,6 +20,7 @@ from nums_b200 import _lib, cuda_compute
 from nums_b200._lib import LIB
 
 MIN_EXTENT = 64   # smaller outputs / vector forms run eagerly (GEMV / split-K kernels)
+MAX_GROUPS = 16   # launches a flush may be cut into to overlap in-flight uploads (see _launch_groups)
 
 
 GemmTerm, GemmProblem = _lib.GemmTerm, _lib.GemmProblem
@@ -30,7 +31,7 @@ class DeferredContraction(object):
     __slots__ = ("terms", "addend", "shape", "flags", "value", "__weakref__")
 
     def __init__(self, terms, shape, flags, addend=None):
-        self.terms = terms        # tuple of (A tensor, lda, B tensor, ldb, k)
+        self.terms = terms        # tuple of (A tensor, lda, B tensor, ldb, k, source block of A, source block of B)
         self.shape = shape        # (m, n)
         self.flags = flags        # (trans_a, trans_b), shared by all terms
         self.addend = addend      # concrete (m, n) float64 tensor or None
@@ -66,13 +67,13 @@ class ContractionQueue(object):
         k2, n = int(a2_shape[0]), int(a2_shape[1])
         if k != k2 or m < MIN_EXTENT or n < MIN_EXTENT or k < 1:
             return None
-        x = cuda_compute._operand(a1, a1_shape, a1_T)
+        x = cuda_compute._operand(a1, a1_shape, a1_T)     # metadata only: no kernel, no wait for uploads
         y = cuda_compute._operand(a2, a2_shape, a2_T)
         A, ta, lda = cuda_compute._as_matrix(x, m, k)
         B, tb, ldb = cuda_compute._as_matrix(y, k, n)
         if not (_dmma_ok(A, lda) and _dmma_ok(B, ldb)):
             return None
-        return self._register(DeferredContraction(((A, lda, B, ldb, k),), (m, n), (bool(ta), bool(tb))))
+        return self._register(DeferredContraction(((A, lda, B, ldb, k, a1, a2),), (m, n), (bool(ta), bool(tb))))
 
     def add(self, x, y, x_shape, y_shape, x_T, y_T):
         """Lazy x + y when at least one side is an unmaterialised contraction of the same shape."""
@@ -125,28 +126,84 @@ class ContractionQueue(object):
         by_flags = {}
         for d in alive:
             by_flags.setdefault(d.flags, []).append(d)
-        stream = cuda_compute._stream()
         for (ta, tb), group in by_flags.items():
-            nterms = sum(len(d.terms) for d in group)
-            problems = (GemmProblem * len(group))()
-            terms = (GemmTerm * nterms)()
-            cursor = 0
-            for i, d in enumerate(group):
-                m, n = d.shape
-                out = cuda_compute._empty((m, n), np.float64)
-                d.value = out
-                pr = problems[i]
-                pr.C = out.data_ptr()
-                pr.Cin = d.addend.data_ptr() if d.addend is not None else None
-                pr.ldc, pr.ldcin, pr.m, pr.n = n, n, m, n
-                pr.term_begin, pr.term_count = cursor, len(d.terms)
-                for (A, lda, B, ldb, k) in d.terms:
-                    tm = terms[cursor]
-                    tm.A, tm.B, tm.lda, tm.ldb, tm.k = A.data_ptr(), B.data_ptr(), lda, ldb, k
-                    cursor += 1
-            device = group[0].value.device
-            LIB.call_ws(LIB.dll.nums_gemm_grouped, device,
-                        ((_lib.F64, int(ta), int(tb), len(group), problems, nterms, terms), (stream,)))
-            for d in group:      # operands may be released now; the stream keeps the ordering
-                d.terms = ()
-                d.addend = None
+            launches = self._launch_groups(group)
+            for chunk, upto in launches:
+                self._launch(ta, tb, chunk, upto, len(launches) > 1)
+
+    @staticmethod
+    def _need(d):
+        """Latest in-flight upload ((sequence, event) or None) among the operands of a contraction."""
+        latest = None
+        for term in d.terms:
+            for src in term[5:]:
+                tag = getattr(src, "_nums_ready", None)
+                if tag is not None and (latest is None or tag[0] > latest[0]):
+                    latest = tag
+        return latest
+
+    def _launch_groups(self, group):
+        """Split one (trans_a, trans_b) class into launch groups by operand readiness.
+
+        Operands uploaded asynchronously (cuda_compute.upload) carry their upload's sequence number;
+        contractions are ordered by the latest upload they read and cut into at most MAX_GROUPS
+        launches (one per set of contractions that become ready together), each waiting only for what
+        it reads, so the GEMM overlaps the rest of the H2D
+        traffic.  With nothing in flight this is a single launch."""
+        stream_key = cuda_compute._stream_unordered()
+        done = cuda_compute._Transfers.awaited.get(stream_key, 0)
+        needs = [self._need(d) for d in group]
+        if all(n is None or n[0] <= done for n in needs):
+            return [(group, None)]
+        seq_of = [n[0] if n is not None and n[0] > done else 0 for n in needs]
+        order = sorted(range(len(group)), key=lambda i: seq_of[i])
+        # runs of contractions that become ready together; neighbouring runs are merged until at most
+        # MAX_GROUPS launches remain
+        runs = []
+        for i in order:
+            if runs and seq_of[runs[-1][-1]] == seq_of[i]:
+                runs[-1].append(i)
+            else:
+                runs.append([i])
+        merge = max(1, -(-len(runs) // MAX_GROUPS))
+        out = []
+        for lo in range(0, len(runs), merge):
+            idx = [i for run in runs[lo:lo + merge] for i in run]
+            tags = [needs[i] for i in idx if seq_of[i]]
+            out.append(([group[i] for i in idx], max(tags, key=lambda t: t[0]) if tags else None))
+        return out
+
+    def _launch(self, ta, tb, group, upto, mark_done):
+        if upto is not None:
+            cuda_compute.await_uploads(upto=upto)
+        stream = cuda_compute._stream_unordered()
+        nterms = sum(len(d.terms) for d in group)
+        problems = (GemmProblem * len(group))()
+        terms = (GemmTerm * nterms)()
+        cursor = 0
+        for i, d in enumerate(group):
+            m, n = d.shape
+            out = cuda_compute._empty((m, n), np.float64)
+            d.value = out
+            pr = problems[i]
+            pr.C = out.data_ptr()
+            pr.Cin = d.addend.data_ptr() if d.addend is not None else None
+            pr.ldc, pr.ldcin, pr.m, pr.n = n, n, m, n
+            pr.term_begin, pr.term_count = cursor, len(d.terms)
+            for term in d.terms:
+                A, lda, B, ldb, k = term[:5]
+                tm = terms[cursor]
+                tm.A, tm.B, tm.lda, tm.ldb, tm.k = A.data_ptr(), B.data_ptr(), lda, ldb, k
+                cursor += 1
+        device = group[0].value.device
+        LIB.call_ws(LIB.dll.nums_gemm_grouped, device,
+                    ((_lib.F64, int(ta), int(tb), len(group), problems, nterms, terms), (stream,)))
+        if mark_done:
+            # lets get_assembled start the D2H of these blocks while later groups still compute
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream())
+            for d in group:
+                d.value._nums_done = done
+        for d in group:      # operands may be released now; the stream keeps the ordering
+            d.terms = ()
+            d.addend = None

@@ -70,6 +70,11 @@ class Comm(object):
     def _as_tensor(x):
         if isinstance(x, np.ndarray):
             return torch.from_numpy(x), True
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            # blocks put() asynchronously may still be on the upload stream: NCCL orders itself after
+            # the current stream only
+            from nums_b200 import cuda_compute
+            cuda_compute.await_uploads()
         return x, False
 
     def broadcast(self, buf, src, group=None, async_op=False):
