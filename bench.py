@@ -547,7 +547,7 @@ def run_gpu(args):
         packed = summa.pack(mine_a, mine_b)      # resident layout: one contiguous panel per k
         del mine_a, mine_b
 
-        flush_every = int(os.environ.get("NUMS_SUMMA_FLUSH", "1"))
+        flush_every = int(os.environ.get("NUMS_SUMMA_FLUSH", "0"))   # 0: SummaMatmul.run's own schedule
 
         def step_resident():
             return summa.run(packed, flush_every=flush_every)
@@ -557,8 +557,13 @@ def run_gpu(args):
             lb = {e: system.put(v) for e, v in b_host.items() if summa.owner_b(*e) == rank}
             c = summa.run(la, lb)
             return {e: system.get(v) for e, v in c.items()}
-        parallelism = ("SUMMA on a %dx%d device grid: one NCCL broadcast of the A(:,k) panel per device row and of the "
-                       "B(k,:) panel per device column per step, prefetched behind the grouped local GEMM" % (pr, pc))
+        exchange = ("each rank pulls the A(:,k) panel of its device row and the B(k,:) panel of its device column out of "
+                    "the owners' symmetric (peer-mapped) memory with copy-engine transfers over NVLink, all queued up front; "
+                    "step 0 and steps 1..7 are two grouped DMMA launches"
+                    if isinstance(packed, multi_gpu._PublishedPanels) else
+                    "one NCCL broadcast of the A(:,k) panel per device row and of the B(k,:) panel per device column per "
+                    "step, prefetched behind the grouped local GEMM")
+        parallelism = "SUMMA on a %dx%d device grid: %s" % (pr, pc, exchange)
 
     # ---- timed: HBM-resident ---------------------------------------------------------------------------
     for _ in range(args.warmup):

@@ -7,9 +7,12 @@ block grid is partitioned over the ranks of one NVSwitch box instead (SURVEY.md 
 
 * ``bop`` / elementwise      : blocks are dealt round-robin, nothing is exchanged;
 * blocked matmul             : SUMMA on a ``pr x pc`` device grid -- C(i,j) lives on rank
-                               ``(i mod pr, j mod pc)``; at step k the owners broadcast the A(:,k)
-                               blocks along device rows and the B(k,:) blocks along device columns
-                               (NCCL broadcasts, prefetched one step ahead of the local GEMMs);
+                               ``(i mod pr, j mod pc)``; step k needs the A(:,k) panel of the owner in
+                               my device row and the B(k,:) panel of the owner in my device column.
+                               On GPUs the resident panels live in symmetric (peer-mapped) memory and
+                               every rank PULLS the panels it needs with copy-engine transfers over
+                               NVLink -- no SM is taken from the DMMA kernel and no rank waits for
+                               another; NCCL broadcasts (prefetched one step ahead) are the fallback;
 * TSQR                       : local Householder R per rank, then a binary tree of
                                ``qr([R_a; R_b])`` over send/recv pairs, R broadcast back;
 * Newton logistic regression : fused local gradient/Hessian, one all-reduce of d + d*d doubles per
@@ -19,6 +22,9 @@ The drivers take a ``system`` (``CudaSystem`` in production; the CPU oracle syst
 tests) and only use its kernel interface plus the ``Comm`` wrapper below, so the host logic is
 testable on CPU with ``world_size = 2`` (tests/test_multi_gpu_cpu.py).
 """
+import os
+import sys
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -142,6 +148,7 @@ class SummaMatmul(object):
         self.my_i = [i for i in range(grid) if i % self.pr == self.r]
         self.my_j = [j for j in range(grid) if j % self.pc == self.c]
         self.trace = None      # set to a list to record (label, k, cuda event) marks (development aid)
+        self._peer = None      # _PeerPanels once set up, False when unavailable
 
     def owner_a(self, i, k):
         return (i % self.pr) * self.pc + (k % self.pc)
@@ -154,8 +161,17 @@ class SummaMatmul(object):
 
     def pack(self, a_blocks, b_blocks):
         """Stack this rank's blocks into one contiguous panel per k, so that a SUMMA step needs ONE
-        broadcast per operand instead of one per block: panels[0][k] holds A(i, k) for i in my_i
-        (owned when k mod pc == c), panels[1][k] holds B(k, j) for j in my_j (owned when k mod pr == r)."""
+        transfer per operand instead of one per block: panels[0][k] holds A(i, k) for i in my_i
+        (owned when k mod pc == c), panels[1][k] holds B(k, j) for j in my_j (owned when k mod pr == r).
+        On GPUs the panels are written into symmetric memory that the peers map (see _PeerPanels)."""
+        first = next(iter(a_blocks.values())) if a_blocks else next(iter(b_blocks.values()))
+        ka = [k for k in range(self.g) if k % self.pc == self.c]
+        kb = [k for k in range(self.g) if k % self.pr == self.r]
+        peer = self._peer_panels(first)
+        if peer is not None:
+            return peer.publish({k: [a_blocks[(i, k)] for i in self.my_i] for k in ka},
+                                {k: [b_blocks[(k, j)] for j in self.my_j] for k in kb})
+
         def stack(blocks):
             first = blocks[0]
             if isinstance(first, np.ndarray):
@@ -164,9 +180,30 @@ class SummaMatmul(object):
             for idx, blk in enumerate(blocks):
                 out[idx].copy_(blk)      # device-to-device placement copy (plumbing, not arithmetic)
             return out
-        pa = {k: stack([a_blocks[(i, k)] for i in self.my_i]) for k in range(self.g) if k % self.pc == self.c}
-        pb = {k: stack([b_blocks[(k, j)] for j in self.my_j]) for k in range(self.g) if k % self.pr == self.r}
+        pa = {k: stack([a_blocks[(i, k)] for i in self.my_i]) for k in ka}
+        pb = {k: stack([b_blocks[(k, j)] for j in self.my_j]) for k in kb}
         return pa, pb
+
+    def _peer_panels(self, like):
+        """The symmetric-memory exchange, set up on first use; None when it does not apply (CPU blocks,
+        one rank, ragged device grid, NUMS_SUMMA_PEER=0, or the set-up failed on any rank)."""
+        if self._peer is None:
+            self._peer = False
+            usable = (isinstance(like, torch.Tensor) and like.is_cuda and self.comm.world > 1
+                      and self.g % self.pr == 0 and self.g % self.pc == 0
+                      and os.environ.get("NUMS_SUMMA_PEER", "1") != "0")
+            if usable:
+                peer = None
+                try:
+                    peer = _PeerPanels(self, like)
+                except Exception as exc:  # noqa: BLE001 -- any failure selects the NCCL broadcasts
+                    sys.stderr.write("[nums_b200] symmetric-memory panels unavailable (%s: %s); using NCCL broadcasts\n"
+                                     % (type(exc).__name__, exc))
+                ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=like.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)     # all ranks take the same path
+                if int(ok.item()) == 1:
+                    self._peer = peer
+        return self._peer or None
 
     def _panels(self, k, packed):
         """Start the (at most two) broadcasts of step k; returns (A panel, B panel, pending works)."""
@@ -186,18 +223,32 @@ class SummaMatmul(object):
         b_panel = {j: buf_b[idx] for idx, j in enumerate(self.my_j)}
         return a_panel, b_panel, [w for w in works if w is not None]
 
-    def run(self, a_blocks, b_blocks=None, flush_every=1):
+    def run(self, a_blocks, b_blocks=None, flush_every=None):
         """Returns {(i, j): block} for the C blocks this rank owns.
 
         `a_blocks` is either the result of ``pack`` or a dict of this rank's A blocks (then `b_blocks`
-        is the dict of B blocks and they are packed here).  The local updates of `flush_every`
-        consecutive k-steps are handed to the system as one deferred chain: one grouped GEMM launch
-        that overlaps with the broadcasts of the following step."""
+        is the dict of B blocks and they are packed here).  The local updates of consecutive k-steps
+        are handed to the system as one deferred chain, i.e. one grouped GEMM launch whose CTAs
+        accumulate the whole chain in registers.  `flush_every` = number of k-steps per launch; the
+        default depends on the exchange: with peer pulls every transfer is queued up front, so step 0
+        is launched alone (it starts as soon as the first panels have landed) and steps 1 .. g-1 as ONE
+        launch -- by then their panels have arrived, and one long launch pays the per-tile prologue
+        (pipeline fill, C read and write) once instead of g - 1 times; with NCCL broadcasts, which are
+        prefetched one step ahead, every step is its own launch."""
         packed = a_blocks if b_blocks is None else self.pack(a_blocks, b_blocks)
+        peer = packed if isinstance(packed, _PublishedPanels) else None
+        if flush_every is None or flush_every <= 0:
+            flush_at = {0, self.g - 1} if peer is not None else set(range(self.g))
+        else:
+            flush_at = {k for k in range(self.g) if (k + 1) % flush_every == 0} | {self.g - 1}
         shape = (self.bs, self.bs)
         c_blocks = {}
         trace = self.trace
-        nxt = self._panels(0, packed)
+        if peer is not None:
+            pulls = peer.owner.pull_all(peer)       # every transfer of this product, queued on the copy streams
+            nxt = pulls[0]
+        else:
+            nxt = self._panels(0, packed)
         for k in range(self.g):
             a_panel, b_panel, works = nxt
             for w in works:
@@ -205,7 +256,8 @@ class SummaMatmul(object):
             if trace is not None:
                 trace.append(("panels_ready", k, self._mark()))
             if k + 1 < self.g:
-                nxt = self._panels(k + 1, packed)   # prefetch while the GEMMs below run
+                # NCCL path: prefetch while the GEMMs below run
+                nxt = pulls[k + 1] if peer is not None else self._panels(k + 1, packed)
             for i in self.my_i:
                 for j in self.my_j:
                     sysk = {"grid_entry": (i, j), "grid_shape": (self.g, self.g)}
@@ -214,16 +266,167 @@ class SummaMatmul(object):
                     prev = c_blocks.get((i, j))
                     c_blocks[(i, j)] = dot if prev is None else self.system.bop(
                         "add", prev, dot, shape, shape, False, False, axes=None, syskwargs=sysk)
-            if hasattr(self.system, "flush") and ((k + 1) % flush_every == 0 or k + 1 == self.g):
+            if hasattr(self.system, "flush") and k in flush_at:
                 self.system.flush()   # one grouped launch for the C += A(:,k) B(k,:) updates so far
                 if trace is not None:
                     trace.append(("gemm_done", k, self._mark()))
+        if peer is not None:
+            peer.owner.product_done()
         return c_blocks
 
     def _mark(self):
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
         return ev
+
+
+class _EventWork(object):
+    """`wait()` orders the current stream after a CUDA event (same call shape as a c10d Work)."""
+    __slots__ = ("event",)
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class _PublishedPanels(object):
+    """Result of ``SummaMatmul.pack`` on the symmetric-memory path."""
+    __slots__ = ("owner", "pa", "pb", "ready")
+
+    def __init__(self, owner, pa, pb, ready):
+        self.owner, self.pa, self.pb, self.ready = owner, pa, pb, ready
+
+
+class _PeerPanels(object):
+    """Panel exchange of SUMMA over NVLink peer memory, driven by the copy engines.
+
+    Every rank keeps its resident panels -- A(my_i, k) for the k it owns, B(k, my_j) likewise -- in one
+    buffer of symmetric memory (``torch.distributed._symmetric_memory``: the same allocation on every
+    rank, mapped into every peer's address space).  A product then needs no collective at all: each
+    rank copies the panels of the owners in its device row / column straight out of their memory
+    with plain device-to-device copies on two copy streams (one per operand, so the row and the
+    column transfer use different engines), all of them queued when the product starts, and the
+    grouped DMMA launch of step k waits for the events of panels k only.  Compared with NCCL
+    broadcasts this takes no SM away from the GEMM (a broadcast channel is a resident CTA whose
+    registers do not fit next to a 288-thread DMMA CTA, so every channel evicts one GEMM CTA), needs
+    no rendezvous between ranks per step, and the data crosses each link once.
+
+    The published panels are immutable while products run.  ``publish`` brackets the rewrite of the
+    buffer with two device-side barriers of the symmetric-memory handle: the first guarantees that no
+    peer is still pulling the previous contents, the second that every rank's new panels are in place.
+    Receive buffers are double-buffered across products, so the pulls of product s + 1 may start while
+    product s still computes.
+    """
+
+    def __init__(self, summa, like):
+        import torch.distributed._symmetric_memory as symm
+        self.s = summa
+        g, bs = summa.g, summa.bs
+        self.device = like.device
+        self.dtype = like.dtype
+        self.na, self.nb = g // summa.pc, g // summa.pr            # panels owned per operand
+        self.shape_a = (len(summa.my_i), bs, bs)
+        self.shape_b = (len(summa.my_j), bs, bs)
+        self.numel_a = int(np.prod(self.shape_a))
+        self.numel_b = int(np.prod(self.shape_b))
+        total = self.na * self.numel_a + self.nb * self.numel_b
+        self.buf = symm.empty(total, dtype=self.dtype, device=self.device)
+        self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        self._recv = [None, None]     # per parity: ({k: A panel}, {k: B panel})
+        self._done = [None, None]     # per parity: event after the last GEMM that read the set
+        self._product = 0
+        self._remote = {}
+
+    def _mine_a(self, k):
+        off = (k // self.s.pc) * self.numel_a
+        return self.buf[off:off + self.numel_a].view(self.shape_a)
+
+    def _mine_b(self, k):
+        off = self.na * self.numel_a + (k // self.s.pr) * self.numel_b
+        return self.buf[off:off + self.numel_b].view(self.shape_b)
+
+    def _remote_view(self, rank, operand, k):
+        key = (rank, operand, k)
+        view = self._remote.get(key)
+        if view is None:
+            if operand == 0:
+                view = self.handle.get_buffer(rank, self.shape_a, self.dtype, (k // self.s.pc) * self.numel_a)
+            else:
+                view = self.handle.get_buffer(rank, self.shape_b, self.dtype,
+                                              self.na * self.numel_a + (k // self.s.pr) * self.numel_b)
+            self._remote[key] = view
+        return view
+
+    def publish(self, a_lists, b_lists):
+        """Write this rank's panels (lists of blocks per owned k) into the symmetric buffer."""
+        from nums_b200 import cuda_compute
+        cuda_compute.await_uploads()
+        self.handle.barrier(channel=0)          # nobody is still reading the previous panels
+        pa, pb = {}, {}
+        for k, blocks in a_lists.items():
+            pa[k] = self._mine_a(k)
+            for idx, blk in enumerate(blocks):
+                pa[k][idx].copy_(blk)           # device-to-device placement copy (plumbing, not arithmetic)
+        for k, blocks in b_lists.items():
+            pb[k] = self._mine_b(k)
+            for idx, blk in enumerate(blocks):
+                pb[k][idx].copy_(blk)
+        self.handle.barrier(channel=1)          # every rank's panels are in place
+        ready = torch.cuda.Event()
+        ready.record()
+        return _PublishedPanels(self, pa, pb, ready)
+
+    def pull_all(self, published):
+        """Queue every panel transfer of one product; returns per k (A panel, B panel, works)."""
+        s = self.s
+        parity = self._product & 1
+        if self._recv[parity] is None:
+            self._recv[parity] = (
+                {k: torch.empty(self.shape_a, dtype=self.dtype, device=self.device)
+                 for k in range(s.g) if k % s.pc != s.c},
+                {k: torch.empty(self.shape_b, dtype=self.dtype, device=self.device)
+                 for k in range(s.g) if k % s.pr != s.r})
+        recv_a, recv_b = self._recv[parity]
+        for stream in self.streams:
+            stream.wait_event(published.ready)
+            if self._done[parity] is not None:
+                stream.wait_event(self._done[parity])     # the product that last read this receive set
+        out = []
+        for k in range(s.g):
+            works = []
+            src_a = s.r * s.pc + (k % s.pc)
+            if src_a == s.comm.rank:
+                buf_a = published.pa[k]
+            else:
+                buf_a = recv_a[k]
+                with torch.cuda.stream(self.streams[0]):
+                    buf_a.copy_(self._remote_view(src_a, 0, k), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                works.append(_EventWork(ev))
+            src_b = (k % s.pr) * s.pc + s.c
+            if src_b == s.comm.rank:
+                buf_b = published.pb[k]
+            else:
+                buf_b = recv_b[k]
+                with torch.cuda.stream(self.streams[1]):
+                    buf_b.copy_(self._remote_view(src_b, 1, k), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                works.append(_EventWork(ev))
+            out.append(({i: buf_a[idx] for idx, i in enumerate(s.my_i)},
+                        {j: buf_b[idx] for idx, j in enumerate(s.my_j)}, works))
+        return out
+
+    def product_done(self):
+        parity = self._product & 1
+        ev = torch.cuda.Event()
+        ev.record()
+        self._done[parity] = ev
+        self._product += 1
 
 
 # ---------------------------------------------------------------------------------------------
