@@ -213,6 +213,16 @@ int nums_inv(int dtype, int64_t n, const void* A, int64_t lda, void* Ainv, int64
 int nums_cholesky(int dtype, int64_t n, const void* A, int64_t lda, void* L, int64_t ldl,
                   int32_t* info, void* ws, size_t ws_bytes, void* stream);
 
+/* Small-matrix stage of the Gram path of qr (np.linalg.qr, numpy_compute.py:240-246, for tall
+ * float64 blocks): from G = A^T A (n <= 128, lower triangle read) one launch writes L = chol(G),
+ * R = L^T (the qr mode='r' result), L^-1 (any of the three may be NULL) and
+ * stats[5] = {info, |L|_1, |L|_inf, |L^-1|_1, |L^-1|_inf} (device doubles; info > 0: G not
+ * numerically positive definite at that step, nothing else written).  The caller accepts R when
+ * sqrt(|L|_1 |L|_inf |L^-1|_1 |L^-1|_inf) >= cond_2(A) is small and otherwise refines or falls
+ * back to nums_qr. */
+int nums_gram_factor(int64_t n, const void* G, int64_t ldg, void* L, int64_t ldl, void* R, int64_t ldr,
+                     void* Linv, int64_t ldi, double* stats, void* stream);
+
 /* Full SVD of a square n x n matrix by one-sided Jacobi (np.linalg.svd, :251-254):
  * A = U diag(S) Vt, S descending. */
 int nums_svd(int dtype, int64_t n, const void* A, int64_t lda, void* U, void* S, void* Vt,

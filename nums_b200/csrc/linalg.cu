@@ -331,6 +331,121 @@ cholesky_kernel(const T* __restrict__ A, int64_t lda, int n, T* __restrict__ out
 
 
 // =====================================================================================
+// Gram-matrix QR, small-matrix stage: Cholesky + triangular inverse + condition bound, one launch
+// =====================================================================================
+// For the Gram path of qr (cuda_compute.qr_r_ex): given G = A^T A (n <= 128) produce L = chol(G),
+// R = L^T, L^-1 and stats = {info, |L|_1, |L|_inf, |L^-1|_1, |L^-1|_inf}, the four norms of the
+// rigorous bound cond_2(A) <= sqrt(|L|_1 |L|_inf |L^-1|_1 |L^-1|_inf).  Everything lives in one
+// n x (n+1) shared-memory array: L in the lower triangle, (L^-1)^T in the strictly upper part
+// shifted right by one column.  Four lanes share each row / column dot product, so the 2n
+// dependent steps cost a few hundred cycles each: ~60 us instead of the ~1.1 ms the separate
+// cholesky + general inverse + norm-reduction launches took.
+constexpr int kGfMaxN = 128;
+constexpr int kGfThreads = 4 * kGfMaxN;
+
+__global__ void __launch_bounds__(kGfThreads, 1)
+gram_factor_kernel(const double* __restrict__ G, int64_t ldg, int n, double* __restrict__ L, int64_t ldl,
+                   double* __restrict__ R, int64_t ldr, double* __restrict__ Linv, int64_t ldi,
+                   double* __restrict__ stats) {
+  extern __shared__ __align__(16) double gf[];
+  __shared__ double pivot;
+  __shared__ double sums[4][kGfMaxN];
+  const int pitch = n + 1;
+  const int tid = threadIdx.x, row = tid >> 2, q = tid & 3;
+  for (int e = tid; e < n * n; e += kGfThreads) {
+    const int i = e / n, c = e - i * n;
+    if (c <= i) gf[i * pitch + c] = G[(int64_t)i * ldg + c];
+  }
+  __syncthreads();
+
+  // ---- left-looking Cholesky: column k of L from rows k.. of (G - L[:, :k] L[k, :k]^T) ------------------
+  int failed = 0;
+  for (int k = 0; k < n; ++k) {
+    const bool active = row >= k && row < n;
+    double acc = 0.0;
+    if (active) {
+      const double* li = gf + row * pitch;
+      const double* lk = gf + k * pitch;
+      for (int j = q; j < k; j += 4) acc = fma(li[j], lk[j], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    const double v = active ? gf[row * pitch + k] - acc : 0.0;
+    if (row == k && q == 0) pivot = v;
+    __syncthreads();
+    const double pv = pivot;
+    if (!(pv > 0.0)) {      // same value in every thread: uniform exit
+      failed = k + 1;
+      break;
+    }
+    const double d = sqrt(pv);
+    if (active && q == 0) gf[row * pitch + k] = (row == k) ? d : v / d;
+    __syncthreads();
+  }
+  if (failed) {
+    if (tid == 0) {
+      stats[0] = (double)failed;
+      stats[1] = stats[2] = stats[3] = stats[4] = 0.0;
+    }
+    return;
+  }
+
+  // ---- X = L^-1 by forward substitution, one column per 4-lane group; X[i][j] -> gf[j][i + 1] -----------
+  {
+    const int col = row;                       // column of X owned by this group
+    const int first = (tid >> 5) * 8;          // smallest column in this warp: uniform loop bounds
+    for (int i = first; i < n; ++i) {
+      double acc = 0.0;
+      const bool mine = col < n && i > col;
+      if (mine) {
+        const double* li = gf + i * pitch;
+        const double* xj = gf + col * pitch + 1;
+        for (int k = col + q; k < i; k += 4) acc = fma(li[k], xj[k], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (col < n && i >= col && q == 0) {
+        const double lii = gf[i * pitch + i];
+        gf[col * pitch + i + 1] = (i == col) ? 1.0 / lii : -acc / lii;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- norms: row and column abs-sums of L and X ---------------------------------------------------------
+  {
+    const int what = tid / n, t = tid - what * n;   // 0: L rows, 1: L columns, 2: X rows, 3: X columns
+    if (what < 4) {
+      double acc = 0.0;
+      if (what == 0) for (int j = 0; j <= t; ++j) acc += fabs(gf[t * pitch + j]);
+      else if (what == 1) for (int i = t; i < n; ++i) acc += fabs(gf[i * pitch + t]);
+      else if (what == 2) for (int j = 0; j <= t; ++j) acc += fabs(gf[j * pitch + t + 1]);
+      else for (int i = t; i < n; ++i) acc += fabs(gf[t * pitch + i + 1]);
+      sums[what][t] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid < 4) {
+    double top = 0.0;
+    for (int t = 0; t < n; ++t) top = fmax(top, sums[tid][t]);
+    // |M|_1 = max column sum, |M|_inf = max row sum
+    const int slot = tid == 0 ? 2 : tid == 1 ? 1 : tid == 2 ? 4 : 3;
+    stats[slot] = top;
+    if (tid == 0) stats[0] = 0.0;
+  }
+  for (int e = tid; e < n * n; e += kGfThreads) {
+    const int i = e / n, c = e - i * n;
+    const double l = (c <= i) ? gf[i * pitch + c] : 0.0;           // L[i][c]
+    const double lt = (c >= i) ? gf[c * pitch + i] : 0.0;          // R[i][c] = L[c][i]
+    const double x = (c <= i) ? gf[c * pitch + i + 1] : 0.0;       // X[i][c]
+    if (L) L[(int64_t)i * ldl + c] = l;
+    if (R) R[(int64_t)i * ldr + c] = lt;
+    if (Linv) Linv[(int64_t)i * ldi + c] = x;
+  }
+}
+
+// =====================================================================================
 // SVD of a square matrix: one-sided Jacobi (Hestenes), one CTA
 // =====================================================================================
 // Works on At (row j = column j of A) and Vt (row j = column j of V) in global scratch (L2
@@ -488,6 +603,20 @@ extern "C" int nums_cholesky(int dtype, int64_t n, const void* A, int64_t lda, v
   if (dtype == NUMS_F32)
     return run_single_cta<float>(cholesky_kernel<float>, n, static_cast<const float*>(A), lda, static_cast<float*>(L), ldl, info, ws, ws_bytes, s, "cholesky");
   NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "cholesky: dtype %s", dtype_name(dtype));
+}
+
+extern "C" int nums_gram_factor(int64_t n, const void* G, int64_t ldg, void* L, int64_t ldl, void* R, int64_t ldr,
+                                void* Linv, int64_t ldi, double* stats, void* stream) {
+  using namespace nums;
+  NUMS_REQUIRE(n >= 1 && n <= kGfMaxN, "gram_factor: n = %lld outside the supported range [1, %d]", (long long)n, kGfMaxN);
+  NUMS_REQUIRE(G && stats, "gram_factor: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t smem = (size_t)n * (n + 1) * sizeof(double);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(gram_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gram_factor_kernel<<<1, kGfThreads, smem, s>>>(static_cast<const double*>(G), ldg, (int)n, static_cast<double*>(L), ldl,
+                                                 static_cast<double*>(R), ldr, static_cast<double*>(Linv), ldi, stats);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
 }
 
 extern "C" int nums_svd(int dtype, int64_t n, const void* A, int64_t lda, void* U, void* S, void* Vt,

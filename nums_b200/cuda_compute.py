@@ -789,29 +789,39 @@ def _norm_1_inf(t):
     return out
 
 
+GRAM_FACTOR_FUSED_MAX = 128   # nums_gram_factor: Cholesky + triangular inverse + norms in one launch
+
+
 def _gram_factor(a):
-    """Cholesky factor L (lower) of a^T a, its inverse, and a rigorous bound on cond_2(a):
+    """Cholesky factor L (lower) of a^T a, its inverse, R = L^T and a rigorous bound on cond_2(a):
     cond_2(a) = cond_2(L) <= sqrt(|L|_1 |L|_inf |L^-1|_1 |L^-1|_inf)   (|M|_2^2 <= |M|_1 |M|_inf),
     which is tight for the nearly diagonal factors of well-conditioned blocks (a Frobenius bound
-    would be off by a factor n).  Returns (L, Linv, kappa_bound); the bound is inf if the Gram matrix
-    is not numerically positive definite.  One 40-byte read-back."""
+    would be off by a factor n).  Returns (L, Linv, R, kappa_bound); the bound is inf if the Gram
+    matrix is not numerically positive definite.  One 40-byte read-back."""
     m, n = a.shape
     gram = _empty((n, n), np.float64)
     gemm_into(gram, a, True, n, a, False, n, n, n, m)
     low = _empty((n, n), np.float64)
-    info = _empty((), np.int32)
-    LIB.call_ws(LIB.dll.nums_cholesky, a.device,
-                ((_lib.F64, n, gram.data_ptr(), n, low.data_ptr(), n, info.data_ptr()), (_stream(),)))
-    low_inv = _inv_nocheck(low)
     stats = _empty((5,), np.float64)
-    _copy_into(stats[0], info)
-    for i, v in enumerate(_norm_1_inf(low) + _norm_1_inf(low_inv)):
-        _copy_into(stats[1 + i], v)
+    if n <= GRAM_FACTOR_FUSED_MAX:
+        low_inv = _empty((n, n), np.float64)
+        upper = _empty((n, n), np.float64)
+        LIB.check(LIB.dll.nums_gram_factor(n, gram.data_ptr(), n, low.data_ptr(), n, upper.data_ptr(), n,
+                                           low_inv.data_ptr(), n, stats.data_ptr(), _stream()))
+    else:
+        info = _empty((), np.int32)
+        LIB.call_ws(LIB.dll.nums_cholesky, a.device,
+                    ((_lib.F64, n, gram.data_ptr(), n, low.data_ptr(), n, info.data_ptr()), (_stream(),)))
+        low_inv = _inv_nocheck(low)
+        upper = _materialize(_transpose_view(low))
+        _copy_into(stats[0], info)
+        for i, v in enumerate(_norm_1_inf(low) + _norm_1_inf(low_inv)):
+            _copy_into(stats[1 + i], v)
     failed, l1, linf, i1, iinf = (float(v) for v in stats.cpu())   # 40-byte D2H, the one sync of this path
     bound = l1 * linf * i1 * iinf
     if failed != 0 or not np.isfinite(bound):
-        return low, low_inv, float("inf")
-    return low, low_inv, float(np.sqrt(bound))
+        return low, low_inv, upper, float("inf")
+    return low, low_inv, upper, float(np.sqrt(bound))
 
 
 def qr_r_ex(arr):
@@ -831,15 +841,15 @@ def qr_r_ex(arr):
                and m >= QR_GRAM_MIN_ASPECT * n and m >= 1024 and arr.data_ptr() % 16 == 0)
     if not gram_ok:
         return _householder_r(arr), None
-    low, low_inv, kappa = _gram_factor(arr)
+    low, low_inv, upper, kappa = _gram_factor(arr)
     if kappa <= QR_GRAM_ACCEPT_KAPPA:
         QR_STATS["gram"] += 1
-        return _materialize(_transpose_view(low)), kappa
+        return upper, kappa
     if kappa <= QR_GRAM_REFINE_KAPPA:
         # CholeskyQR2: Q1 = A L^-T, second Gram factor, R = (L1 L2)^T
         q1 = _empty((m, n), np.float64)
         gemm_into(q1, arr, False, n, low_inv, True, n, m, n, n)
-        low2, _low2_inv, kappa2 = _gram_factor(q1)
+        low2, _low2_inv, _upper2, kappa2 = _gram_factor(q1)
         if kappa2 <= QR_GRAM_ACCEPT_KAPPA:
             prod = _empty((n, n), np.float64)
             gemm_into(prod, low, False, n, low2, False, n, n, n, n)

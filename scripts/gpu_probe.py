@@ -161,6 +161,29 @@ def main():
             record("qr_r_%dx%d" % (m, n), ms=med * 1e3, tflops_med=flops / med / 1e12, wall_s=time.time() - t0)
             del X
 
+    if "qrparts" in which:       # where one Gram-path qr_r of a 2M x 128 block spends its time
+        from nums_b200 import _lib
+        LIB = _lib.LIB
+        m, n = 2_097_152, 128
+        X = torch.randn((m, n), dtype=torch.float64, device=dev)
+        gram = torch.empty((n, n), dtype=torch.float64, device=dev)
+        med, _ = timeit(lambda: cc.gemm_into(gram, X, True, n, X, False, n, n, n, m), iters=5, warmup=2)
+        record("qrparts_gram_gemm", ms=med * 1e3, tflops=2.0 * m * n * n / med / 1e12)
+        low = torch.empty((n, n), dtype=torch.float64, device=dev)
+        info = torch.empty((), dtype=torch.int32, device=dev)
+        med, _ = timeit(lambda: LIB.call_ws(LIB.dll.nums_cholesky, X.device, ((_lib.F64, n, gram.data_ptr(), n, low.data_ptr(), n,
+                                                                                 info.data_ptr()), (cc._stream(),))), flush=False)
+        record("qrparts_cholesky_128", us=med * 1e6)
+        med, _ = timeit(lambda: cc._inv_nocheck(low), flush=False)
+        record("qrparts_inv_128", us=med * 1e6)
+        med, _ = timeit(lambda: cc._norm_1_inf(low), flush=False)
+        record("qrparts_norms", us=med * 1e6)
+        med, _ = timeit(lambda: cc._gram_factor(X), iters=5, warmup=2)
+        record("qrparts_gram_factor_total", ms=med * 1e3)
+        med, _ = timeit(lambda: cc.qr_r(X), iters=5, warmup=2)
+        record("qrparts_qr_r_total", ms=med * 1e3)
+        del X
+
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/probe.json", "w") as f:
         json.dump(OUT, f, indent=1)

@@ -545,6 +545,42 @@ def test_qr_concatenated_inputs(cuda_system, oracle):
     assert rel_fro(_canon(got), _canon(want)) <= GEMM_TOL
 
 
+@pytest.mark.parametrize("n", [1, 2, 7, 28, 64, 127, 128])
+def test_gram_factor_entry(cuda_system, n):
+    """nums_gram_factor (the small-matrix stage of the Gram QR path): L, R = L^T, L^-1 and the four
+    norms against NumPy; a non-positive-definite input reports the failing step."""
+    import torch
+    from nums_b200 import _lib
+    LIB = _lib.LIB
+    rng = np.random.default_rng(64)
+    A = rng.standard_normal((4 * n + 8, n))
+    G = A.T @ A
+    dev = cuda_system.put(G)
+    outs = [torch.empty((n, n), dtype=torch.float64, device=dev.device) for _ in range(3)]
+    stats = torch.empty((5,), dtype=torch.float64, device=dev.device)
+    stream = torch.cuda.current_stream().cuda_stream
+    LIB.check(LIB.dll.nums_gram_factor(n, dev.data_ptr(), n, outs[0].data_ptr(), n, outs[1].data_ptr(), n,
+                                       outs[2].data_ptr(), n, stats.data_ptr(), stream))
+    L, R, Linv = (t.cpu().numpy() for t in outs)
+    info, l1, linf, i1, iinf = stats.cpu().numpy()
+    want = np.linalg.cholesky(G)
+    assert info == 0
+    assert rel_fro(L, want) <= 1e-12
+    assert np.array_equal(R, L.T)
+    assert rel_fro(Linv, np.linalg.inv(want)) <= 1e-11
+    assert np.array_equal(np.triu(L, 1), np.zeros((n, n))) and np.array_equal(np.triu(Linv, 1), np.zeros((n, n)))
+    for got, ref in ((l1, np.linalg.norm(want, 1)), (linf, np.linalg.norm(want, np.inf)),
+                     (i1, np.linalg.norm(np.linalg.inv(want), 1)), (iinf, np.linalg.norm(np.linalg.inv(want), np.inf))):
+        assert abs(got - ref) <= 1e-11 * ref
+    assert np.sqrt(l1 * linf * i1 * iinf) >= np.linalg.cond(A) * (1 - 1e-10)     # the bound really bounds
+    if n >= 2:
+        bad = G.copy()
+        bad[n - 1, n - 1] = -1.0
+        LIB.check(LIB.dll.nums_gram_factor(n, cuda_system.put(bad).data_ptr(), n, outs[0].data_ptr(), n, outs[1].data_ptr(),
+                                           n, outs[2].data_ptr(), n, stats.data_ptr(), stream))
+        assert stats.cpu().numpy()[0] == n
+
+
 @pytest.mark.parametrize("n", [1, 2, 9, 28, 64, 128, 200])
 def test_inv_cholesky(cuda_system, oracle, n):
     rng = np.random.default_rng(63)
