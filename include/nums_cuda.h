@@ -213,6 +213,24 @@ int nums_inv(int dtype, int64_t n, const void* A, int64_t lda, void* Ainv, int64
 int nums_cholesky(int dtype, int64_t n, const void* A, int64_t lda, void* L, int64_t ldl,
                   int32_t* info, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- delimited text ingest ------------------------------------------------
+ * Device-side replacement of read_csv_block (nums/core/systems/filesystem.py:157-212): the bytes
+ * [first, stop) of `text` (device memory, 16-byte aligned, readable up to `stop` rounded up to a
+ * multiple of 32) are the whole lines of one chunk, chosen by the caller with the reference's
+ * rule (:196-211).  nums_csv_index counts them; nums_csv_parse converts every field with the
+ * dtype's converter (:160-190: float(x), np.int64(x), int(float(x)), bool(int(x))) into the
+ * row-major rows x cols block `out`.
+ * summary (device int64[4]) = {lines, fields, status, byte offset of the first offending field};
+ * status is NUMS_CSV_OK, _INVALID (the reference raises ValueError), _UNSUPPORTED (valid for the
+ * reference, not handled: hex float, lone '\r', undecidable literal of > 19 digits) or _RAGGED
+ * (rows of different lengths; np.array raises ValueError).  nums_csv_index leaves per-tile offsets
+ * in `ws`, which nums_csv_parse reads: same workspace, same stream, no launch in between. */
+enum { NUMS_CSV_OK = 0, NUMS_CSV_INVALID = 1, NUMS_CSV_UNSUPPORTED = 2, NUMS_CSV_RAGGED = 3 };
+int nums_csv_index(const void* text, int64_t first, int64_t stop, int delimiter, int64_t* summary,
+                   void* ws, size_t ws_bytes, void* stream);
+int nums_csv_parse(const void* text, int64_t first, int64_t stop, int delimiter, int dtype, int64_t rows,
+                   int64_t cols, void* out, int64_t* summary, const void* ws, void* stream);
+
 /* Small-matrix stage of the Gram path of qr (np.linalg.qr, numpy_compute.py:240-246, for tall
  * float64 blocks): from G = A^T A (n <= 128, lower triangle read) one launch writes L = chol(G),
  * R = L^T (the qr mode='r' result), L^-1 (any of the three may be NULL) and

@@ -20,7 +20,8 @@ LIB = os.path.join(HERE, "libnumscuda.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 # Elementwise files keep IEEE add/mul un-contracted so results are bit-identical to NumPy's.
-PER_FILE = {"bop.cu": ["-fmad=false"], "uop.cu": ["-fmad=false"], "reduce.cu": ["-fmad=false"]}
+PER_FILE = {"bop.cu": ["-fmad=false"], "uop.cu": ["-fmad=false"], "reduce.cu": ["-fmad=false"],
+            "csv.cu": ["-fmad=false"]}
 
 
 def _nvcc():
@@ -44,7 +45,7 @@ def sources():
 
 
 def headers():
-    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     hs.append(os.path.join(ROOT, "include", "nums_cuda.h"))
     return sorted(hs)
 

@@ -520,3 +520,50 @@ def newton(app, model, beta, X, y, tol, max_iter):
         if app.max(app.abs(g)) <= tol:
             break
     return beta, iters
+
+
+class FileSystem(object):
+    """``FileSystem.read_csv`` of the reference (filesystem.py:402-439): the file is cut into
+    ``num_workers`` byte ranges (``Batch.from_num_batches``, storage/utils.py:30-62), every range goes
+    to the registered ``read_csv_block`` kernel (one call per range, ``num_returns = 2``), and each
+    non-empty result becomes a single-block ``BlockArray``.  ``read_csv_block`` defaults to the device
+    parser (``cuda_compute.read_csv_block``); the CPU tests pass the oracle's."""
+
+    def __init__(self, system, read_csv_block=None):
+        self.system = system
+        if read_csv_block is None:
+            from nums_b200 import cuda_compute
+            read_csv_block = cuda_compute.read_csv_block
+        self.system.register("read_csv_block", read_csv_block, {})
+
+    @staticmethod
+    def byte_ranges(total_size, num_batches):
+        batch_size = (total_size + num_batches - 1) // num_batches
+        if total_size < batch_size:
+            return [[0, total_size]]
+        starts = list(range(0, total_size, batch_size))
+        out = [starts[i:i + 2] for i in range(int(total_size / batch_size))]
+        if len(out[-1]) == 1:
+            out[-1].append(total_size)
+        if out[-1][1] != total_size:
+            out.append([out[-1][1], total_size])
+        return out
+
+    def read_csv(self, filename, dtype=np.float64, delimiter=",", has_header=False, num_workers=4):
+        import os
+        ranges = self.byte_ranges(os.path.getsize(filename), num_workers)
+        parts = []
+        for i, (file_start, file_end) in enumerate(ranges):
+            parts.append(self.system.call("read_csv_block", filename, file_start, file_end, dtype, delimiter, has_header,
+                                          syskwargs={"grid_entry": (i,), "grid_shape": (num_workers,),
+                                                     "options": {"num_returns": 2}}))
+        arrays = []
+        for block_oid, shape in parts:
+            shape = tuple(int(v) for v in self.system.get(shape)) if not isinstance(shape, tuple) else shape
+            if shape[0] == 0:
+                continue
+            grid = ArrayGrid(shape, shape, np.dtype(dtype).type.__name__)
+            arr = BlockArray(grid, self.system)
+            arr.blocks[next(iter(grid.get_entry_iterator()))].oid = block_oid
+            arrays.append(arr)
+        return arrays

@@ -153,7 +153,11 @@ def upload(value, dtype=None):
         return host.to(_device()).view(())
     if not arr.flags.writeable:
         arr = arr.copy()
-    host = torch.from_numpy(arr)
+    return _upload_tensor(torch.from_numpy(arr))
+
+
+def _upload_tensor(host):
+    """Host tensor (any torch dtype, e.g. raw uint8 file bytes) -> device tensor."""
     if host.numel() * host.element_size() >= (1 << 20) and host.is_pinned():
         # asynchronous, on the upload stream; consumers order themselves through _stream()
         device = _device()
@@ -950,3 +954,109 @@ def lr_grad_hess_blocks(x_blocks, y_blocks, beta):
         part = lr_grad_hess(x, y, beta)
         total = part if total is None else elementwise("add", total, part)
     return total
+
+
+# ---------------------------------------------------------------------------------------------
+# delimited text ingest
+# ---------------------------------------------------------------------------------------------
+_CSV_STATUS = {1: "could not convert field to %s", 2: "field is valid for the reference but not supported by cuda_compute "
+               "(hexadecimal float, lone carriage return, or a literal of more than 19 digits that cannot be decided) for %s",
+               3: "rows have different numbers of fields (%s block)"}
+
+
+def _csv_dtype(dtype):
+    """The reference's converter choice (filesystem.py:169-190) -> (output dtype, kernel dtype code)."""
+    if dtype is float:
+        return np.dtype(np.float64)
+    if dtype is int or dtype is bool:
+        # int -> int(float(x)) into int64, bool -> Python bool(): neither is what the typed kernels implement
+        raise NotImplementedError("read_csv_block: pass a NumPy dtype (float64, float32, int64, int32, bool_)")
+    dt = np.dtype(dtype)
+    if dt not in (np.dtype(np.float64), np.dtype(np.float32), np.dtype(np.int64), np.dtype(np.int32), np.dtype(np.bool_)):
+        raise NotImplementedError("read_csv_block: dtype %s" % dt)
+    return dt
+
+
+def _find_byte(view, value, start):
+    """Index of the first `value` in the uint8 array `view` at or after `start`, or -1."""
+    step = 1 << 16
+    n = view.shape[0]
+    while start < n:
+        hits = np.flatnonzero(view[start:start + step] == value)
+        if hits.size:
+            return start + int(hits[0])
+        start += step
+    return -1
+
+
+def read_csv_block(filename, file_start, file_end, dtype, delimiter, has_header):
+    """``read_csv_block`` of the reference (filesystem.py:157-212) with the parsing on the device.
+
+    The chunk's lines are chosen exactly as the reference's text-mode loop does: if ``file_start``
+    is not 0, everything up to and including the first newline at or after it is skipped (:198-201);
+    then every line that *starts* before ``file_end`` is taken (:203-204), the header being dropped in
+    the first chunk (:205-207).  The bytes of those lines are read straight into page-locked memory,
+    uploaded, and split / converted by ``nums_csv_index`` + ``nums_csv_parse``.  Returns
+    ``(block, shape)`` like the reference (:211-212); malformed input raises ``ValueError``.
+    """
+    import os
+    dt = _csv_dtype(dtype)
+    if not isinstance(delimiter, str) or len(delimiter.encode()) != 1:
+        raise NotImplementedError("read_csv_block: single-byte delimiters only")
+    delim = delimiter.encode()[0]
+    size = os.path.getsize(filename)
+    file_start, file_end = int(file_start), min(int(file_end), size)
+    empty = (upload(np.array([], dtype=dt)), (0,))
+    if file_start >= file_end:
+        return empty
+    slack = 1 << 16
+    with open(filename, "rb") as fh:
+        while True:
+            want = min(size, file_end + slack) - file_start
+            pinned = torch.empty(((want + 63) // 32 * 32,), dtype=torch.uint8, pin_memory=True)
+            view = pinned.numpy()
+            fh.seek(file_start)
+            got = fh.readinto(memoryview(view)[:want])
+            if got != want:
+                raise IOError("short read from %s" % filename)
+            view[want:] = 0
+            # the last line of the chunk is the one holding byte file_end - 1; it ends at its newline
+            last_nl = _find_byte(view[:want], 10, file_end - 1 - file_start)
+            if last_nl >= 0 or file_start + want == size:
+                break
+            slack *= 8      # a very long line: read further
+    stop = last_nl + 1 if last_nl >= 0 else want
+    first = 0
+    if file_start != 0:
+        nl = _find_byte(view[:stop], 10, 0)
+        if nl < 0:
+            return empty
+        first = nl + 1
+    if has_header and file_start == 0:
+        nl = _find_byte(view[:stop], 10, 0)
+        first = nl + 1 if nl >= 0 else stop
+    if first >= stop:
+        return empty
+    line_end = _find_byte(view[:stop], 10, first)
+    line_end = stop if line_end < 0 else line_end
+    cols = int(np.count_nonzero(view[first:line_end] == delim)) + 1
+
+    text = _upload_tensor(pinned)
+    summary = _empty((4,), np.int64)
+    ws = LIB.workspace(text.device, 2 * ((stop - first) // 8192 + 4) * 8)
+    LIB.check(LIB.dll.nums_csv_index(text.data_ptr(), first, stop, delim, summary.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     _stream()))
+    rows, fields, status, where = (int(v) for v in summary.cpu())      # 32-byte read-back: the block's shape
+    if status == 0 and fields != rows * cols:
+        status = 3
+    out = _empty((rows, cols), dt)
+    if status == 0:
+        LIB.check(LIB.dll.nums_csv_parse(text.data_ptr(), first, stop, delim, _lib.dtype_code(dt), rows, cols,
+                                         out.data_ptr(), summary.data_ptr(), ws.data_ptr(), _stream()))
+        rows2, fields2, status, where = (int(v) for v in summary.cpu())
+    if status != 0:
+        at = "" if where >= (1 << 62) else " at byte %d of %s" % (file_start + where, filename)
+        if status == 2:
+            raise NotImplementedError("read_csv_block: " + _CSV_STATUS[2] % dt + at)
+        raise ValueError("read_csv_block: " + _CSV_STATUS[status] % dt + at)
+    return out, (rows, cols)
