@@ -315,7 +315,64 @@ def other_workloads(system, quick):
                       "workload": "indirect_tsqr (Q = X R^-1, R) on 16777216 x 128 float64, 8 row blocks"}
     del X
     torch.cuda.empty_cache()
+    out["csv_ingest"] = csv_workload(system, quick)
     return out
+
+
+def csv_workload(system, quick):
+    """read_csv_block on a HIGGS-shaped text file (29 columns, np.savetxt's %.18e).  Reports
+    GB/s of text for the two kernels alone (text resident in HBM), end to end from the file (page cache ->
+    page-locked buffer -> H2D -> kernels -> shape read-back), and the reference's Python parser on a bounded
+    sample of the same file (1 core)."""
+    import tempfile
+    import torch
+    from nums_b200 import cuda_compute as cc
+    from oracle import csv_oracle
+    rng = np.random.default_rng(9)
+    block_rows, cols = 4000, 29
+    x = rng.standard_normal((block_rows, cols))
+    x[:, 0] = rng.integers(0, 2, block_rows)
+    chunk = "".join(",".join("%.18e" % v for v in row) + "\n" for row in x).encode()
+    repeat = 16 if quick else 64                      # 46 MB / 185 MB of text
+    path = os.path.join(tempfile.mkdtemp(), "higgs_like.csv")
+    with open(path, "wb") as f:
+        for _ in range(repeat):
+            f.write(chunk)
+    size = os.path.getsize(path)
+    rows = block_rows * repeat
+    # end to end, through the public entry point
+    cc.read_csv_block(path, 0, size, np.float64, ",", False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    block, shape = cc.read_csv_block(path, 0, size, np.float64, ",", False)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    assert tuple(shape) == (rows, cols)
+    got = system.get(block)
+    assert np.array_equal(got[:block_rows], x) and np.array_equal(got[-block_rows:], x)   # %.18e round-trips exactly
+    del block, got
+    # kernels alone
+    host = torch.empty(((size + 63) // 32 * 32,), dtype=torch.uint8, pin_memory=True)
+    with open(path, "rb") as f:
+        f.readinto(memoryview(host.numpy())[:size])
+    text = host.cuda()
+    t_kernel = min(cuda_time(lambda: cc.parse_csv_text(text, 0, size, ord(","), np.float64, cols), torch.cuda.synchronize)
+                   for _ in range(3))
+    del text, host
+    # reference parser (oracle port of read_csv_block) on the first ~3 MB
+    sample_end = min(size, 3 << 20)
+    t0 = time.perf_counter()
+    ref, _shape = csv_oracle.read_csv_block(path, 0, sample_end, np.float64, ",", False)
+    t_cpu = time.perf_counter() - t0
+    os.remove(path)
+    return {"value": size / t_kernel / 1e9, "unit": "GB/s of text", "ms": t_kernel * 1e3,
+            "workload": "read_csv_block on %d rows x %d columns of %%.18e text (%.0f MB), float64" % (rows, cols, size / 1e6),
+            "kernels": "nums_csv_index + nums_csv_parse incl. the two 32-byte status read-backs",
+            "e2e_GBps": size / t_e2e / 1e9, "e2e_ms": t_e2e * 1e3,
+            "cpu_baseline": {"value": sample_end / t_cpu / 1e9, "unit": "GB/s of text", "cores": 1, "kind": "port",
+                             "sample": "first %.1f MB (%d rows) through the oracle port of read_csv_block" % (sample_end / 1e6,
+                                                                                                          ref.shape[0])},
+            "parity": "first and last 4000 rows bit-identical to the generated doubles"}
 
 
 def sharded_workloads(system, comm, quick):

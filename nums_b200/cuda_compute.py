@@ -1042,21 +1042,32 @@ def read_csv_block(filename, file_start, file_end, dtype, delimiter, has_header)
     cols = int(np.count_nonzero(view[first:line_end] == delim)) + 1
 
     text = _upload_tensor(pinned)
+    try:
+        return parse_csv_text(text, first, stop, delim, dt, cols)
+    except (ValueError, NotImplementedError) as exc:
+        where = getattr(exc, "offset", None)
+        at = "" if where is None else " at byte %d of %s" % (file_start + where, filename)
+        raise type(exc)(str(exc) + at) from None
+
+
+def parse_csv_text(text, first, stop, delimiter, dtype, cols):
+    """Bytes [first, stop) of the device uint8 tensor ``text`` (whole lines) -> ``(block, shape)``.
+    ``text`` must be readable up to ``stop`` rounded up to a multiple of 32."""
+    dt = np.dtype(dtype)
     summary = _empty((4,), np.int64)
     ws = LIB.workspace(text.device, 2 * ((stop - first) // 8192 + 4) * 8)
-    LIB.check(LIB.dll.nums_csv_index(text.data_ptr(), first, stop, delim, summary.data_ptr(), ws.data_ptr(), ws.numel(),
-                                     _stream()))
+    LIB.check(LIB.dll.nums_csv_index(text.data_ptr(), first, stop, delimiter, summary.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), _stream()))
     rows, fields, status, where = (int(v) for v in summary.cpu())      # 32-byte read-back: the block's shape
     if status == 0 and fields != rows * cols:
         status = 3
     out = _empty((rows, cols), dt)
     if status == 0:
-        LIB.check(LIB.dll.nums_csv_parse(text.data_ptr(), first, stop, delim, _lib.dtype_code(dt), rows, cols,
+        LIB.check(LIB.dll.nums_csv_parse(text.data_ptr(), first, stop, delimiter, _lib.dtype_code(dt), rows, cols,
                                          out.data_ptr(), summary.data_ptr(), ws.data_ptr(), _stream()))
-        rows2, fields2, status, where = (int(v) for v in summary.cpu())
+        _rows, _fields, status, where = (int(v) for v in summary.cpu())
     if status != 0:
-        at = "" if where >= (1 << 62) else " at byte %d of %s" % (file_start + where, filename)
-        if status == 2:
-            raise NotImplementedError("read_csv_block: " + _CSV_STATUS[2] % dt + at)
-        raise ValueError("read_csv_block: " + _CSV_STATUS[status] % dt + at)
+        exc = (NotImplementedError if status == 2 else ValueError)("read_csv_block: " + _CSV_STATUS[status] % dt)
+        exc.offset = None if where >= (1 << 62) else where
+        raise exc
     return out, (rows, cols)
