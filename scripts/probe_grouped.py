@@ -10,7 +10,7 @@ bs = 2048
 shape = (bs, bs)
 
 def run(nprob, nterm, with_cin, distinct_b):
-    A = [torch.randn(shape, dtype=torch.float64, device=dev) for _ in range(nprob * nterm if not distinct_b else 4 * nterm)]
+    A = [torch.randn(shape, dtype=torch.float64, device=dev) for _ in range(nprob * nterm if not distinct_b else (nprob // 4 + 1) * nterm)]
     B = [torch.randn(shape, dtype=torch.float64, device=dev) for _ in range(4 * nterm)]
     prev = [torch.randn(shape, dtype=torch.float64, device=dev) for _ in range(nprob)] if with_cin else None
     def build():
@@ -37,5 +37,10 @@ def run(nprob, nterm, with_cin, distinct_b):
     flops = nprob * nterm * 2.0 * bs ** 3
     print("nprob=%2d nterm=%d cin=%d sharedAB=%d: %.3f ms  %.2f TFLOP/s" % (nprob, nterm, with_cin, distinct_b, ts[2], flops / ts[2] / 1e9), flush=True)
 
-for args in [(16, 1, 0, 1), (16, 1, 1, 1), (16, 2, 1, 1), (16, 8, 0, 1), (8, 1, 1, 1), (64, 8, 0, 0), (16, 1, 0, 0)]:
+cases = [(16, 1, 0, 1), (16, 1, 1, 1), (16, 8, 0, 1), (64, 8, 0, 0)]
+if len(sys.argv) > 1 and sys.argv[1] == "summa":
+    # the two launches of one SUMMA product per rank at N = 8 (8 problems), N = 4 (16) and N = 2 (32):
+    # (problems, terms, addend)   expected pro rata from the 64 x 8 launch
+    cases = [(32, 1, 0, 1), (32, 7, 1, 1), (8, 7, 1, 1)]
+for args in cases:
     run(*args)
