@@ -295,11 +295,12 @@ def other_workloads(system, quick):
     iters_fused = 10
 
     def fused():
-        multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters_fused, cc.lr_grad_hess_blocks)
+        multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters_fused, cc.lr_grad_hess_blocks, step=cc.newton_step)
     t = timed(fused, 2 if quick else 3)
     out["newton_lr_fused"] = {
         "value": t / iters_fused, "unit": "s/iter",
-        "workload": "Newton iteration with the fused gradient+Hessian kernel, 11M x 28 float64, 8 row blocks, 10 iterations",
+        "workload": "Newton iteration = fused gradient+Hessian kernel + fused update kernel, 11M x 28 float64, 8 row blocks, "
+                    "10 iterations, one 16-byte read-back each",
         "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_fused) / 1e9}
     del X, y, xs, ys
 
@@ -448,7 +449,7 @@ def sharded_workloads(system, comm, quick):
     iters = 10
 
     def newton():
-        multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters, cc.lr_grad_hess_blocks)
+        multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters, cc.lr_grad_hess_blocks, step=cc.newton_step)
     t = timed(newton, 2 if quick else 3)
     out["newton_lr_fused"] = {"value": t / iters, "unit": "s/iter",
                               "workload": "Newton LR 11M x 28 float64, 8 row blocks over %d GPU(s), fused g|H kernel + one "

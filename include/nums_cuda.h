@@ -213,6 +213,14 @@ int nums_inv(int dtype, int64_t n, const void* A, int64_t lda, void* Ainv, int64
 int nums_cholesky(int dtype, int64_t n, const void* A, int64_t lda, void* L, int64_t ldl,
                   int32_t* info, void* ws, size_t ws_bytes, void* stream);
 
+/* Newton update of glms.newton (glms.py:362-372: beta <- beta - inv(H) g, stop on max |g| <= tol) in one
+ * launch: gh = d entries of g followed by d*d entries of H (the layout nums_lr_grad_hess writes, after
+ * the cross-block / cross-rank sum); beta_out = beta - H^-1 g by Gauss-Jordan with partial pivoting;
+ * status (device, f64[2]) = {max |g|, info} with info > 0 = zero pivot at that step (np.linalg.inv
+ * would raise LinAlgError).  d <= 128. */
+int nums_newton_step(int64_t d, const double* gh, const double* beta, double* beta_out, double* status,
+                     void* stream);
+
 /* ---- delimited text ingest ------------------------------------------------
  * Device-side replacement of read_csv_block (nums/core/systems/filesystem.py:157-212): the bytes
  * [first, stop) of `text` (device memory, 16-byte aligned, readable up to `stop` rounded up to a

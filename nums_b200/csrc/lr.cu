@@ -538,8 +538,111 @@ int launch_lr(const double* X, int64_t ldx, const double* y, const double* beta,
   return NUMS_OK;
 }
 
+// Newton update of glms.newton (glms.py:362-372) as one single-CTA kernel: from the summed buffer
+// g | H it solves H step = g (Gauss-Jordan on the augmented matrix, partial pivoting like LAPACK's
+// LU behind np.linalg.inv), writes beta_out = beta - step and status = {max |g|, info}.  Replaces the
+// inv / tensordot / sub / abs / max launches and the 4-byte pivot read-back of the interface path with
+// one launch and one 16-byte read-back per iteration.
+constexpr int kNewtonThreads = 256;
+constexpr int kNewtonMaxD = 128;
+
+// max that propagates NaN, like np.max
+__device__ __forceinline__ double max_nan(double a, double b) { return a != a ? a : (b != b ? b : fmax(a, b)); }
+
+__global__ void __launch_bounds__(kNewtonThreads, 1)
+newton_step_kernel(int d, const double* __restrict__ gh, const double* __restrict__ beta,
+                   double* __restrict__ beta_out, double* __restrict__ status) {
+  extern __shared__ __align__(16) double aug[];   // d x (d + 2): [H | g], pitch d + 2
+  __shared__ int piv_row;
+  __shared__ int failed;
+  __shared__ double red[kNewtonThreads / 32];
+  const int pitch = d + 2;
+  const int tid = threadIdx.x;
+  if (tid == 0) failed = 0;
+  for (int e = tid; e < d * d; e += kNewtonThreads) {
+    const int i = e / d, c = e - i * d;
+    aug[i * pitch + c] = gh[d + e];
+  }
+  double gmax = 0.0;
+  for (int i = tid; i < d; i += kNewtonThreads) {
+    const double g = gh[i];
+    aug[i * pitch + d] = g;
+    gmax = max_nan(gmax, fabs(g));
+  }
+  for (int o = 16; o > 0; o >>= 1) gmax = max_nan(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  if ((tid & 31) == 0) red[tid >> 5] = gmax;
+  __syncthreads();
+  for (int k = 0; k < d; ++k) {
+    if (tid < 32) {     // pivot: first maximum of |aug[i][k]|, i >= k
+      double best = -1.0;
+      int bi = k;
+      for (int i = k + tid; i < d; i += 32) {
+        const double a = fabs(aug[i * pitch + k]);
+        if (a > best) {
+          best = a;
+          bi = i;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+          best = ob;
+          bi = oi;
+        }
+      }
+      if (tid == 0) {
+        piv_row = bi;
+        if (!(best > 0.0) && failed == 0) failed = k + 1;
+      }
+    }
+    __syncthreads();
+    const int p = piv_row;
+    if (p != k) {
+      for (int c = k + tid; c <= d; c += kNewtonThreads) {
+        const double a = aug[k * pitch + c];
+        aug[k * pitch + c] = aug[p * pitch + c];
+        aug[p * pitch + c] = a;
+      }
+      __syncthreads();
+    }
+    const double inv_pivot = 1.0 / aug[k * pitch + k];
+    __syncthreads();
+    for (int c = k + tid; c <= d; c += kNewtonThreads) aug[k * pitch + c] *= inv_pivot;
+    __syncthreads();
+    // eliminate column k from every other row (columns k+1 .. d; column k itself is not read again)
+    const int width = d - k;
+    for (int e = tid; e < d * width; e += kNewtonThreads) {
+      const int i = e / width, c = k + 1 + (e - i * width);
+      if (i != k) aug[i * pitch + c] = fma(-aug[i * pitch + k], aug[k * pitch + c], aug[i * pitch + c]);
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < d; i += kNewtonThreads) beta_out[i] = beta[i] - aug[i * pitch + d];
+  if (tid == 0) {
+    double top = red[0];
+    for (int w = 1; w < kNewtonThreads / 32; ++w) top = max_nan(top, red[w]);
+    status[0] = top;
+    status[1] = (double)failed;
+  }
+}
+
 }  // namespace
 }  // namespace nums
+
+extern "C" int nums_newton_step(int64_t d, const double* gh, const double* beta, double* beta_out, double* status,
+                                void* stream) {
+  using namespace nums;
+  NUMS_REQUIRE(d >= 1 && d <= kNewtonMaxD, "newton_step: d = %lld outside the supported range [1, %d]", (long long)d,
+               kNewtonMaxD);
+  NUMS_REQUIRE(gh && beta && beta_out && status, "newton_step: null pointer");
+  const size_t smem = (size_t)d * (d + 2) * sizeof(double);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(newton_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  newton_step_kernel<<<1, kNewtonThreads, smem, static_cast<cudaStream_t>(stream)>>>((int)d, gh, beta, beta_out, status);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
 
 extern "C" int nums_lr_grad_hess(int64_t n, int64_t d, const double* X, int64_t ldx, const double* y,
                                  const double* beta, double* out, void* ws, size_t ws_bytes,

@@ -956,6 +956,21 @@ def lr_grad_hess_blocks(x_blocks, y_blocks, beta):
     return total
 
 
+def newton_step(gh, beta):
+    """One Newton update from the summed ``g | H`` buffer (glms.py:362-372): returns
+    ``(beta - inv(H) g, status)`` where ``status`` is a 2-element device tensor {max |g|, info}.  The
+    caller reads ``status`` back once per iteration (convergence test + singularity check)."""
+    d = beta.shape[0]
+    if gh.shape[0] != d + d * d or gh.dtype != torch.float64 or beta.dtype != torch.float64:
+        raise ValueError("newton_step: expected float64 g | H of %d entries" % (d + d * d))
+    gh = gh if gh.is_contiguous() else _materialize(gh)
+    beta = beta if beta.is_contiguous() else _materialize(beta)
+    out = _empty((d,), np.float64)
+    status = _empty((2,), np.float64)
+    LIB.check(LIB.dll.nums_newton_step(d, gh.data_ptr(), beta.data_ptr(), out.data_ptr(), status.data_ptr(), _stream()))
+    return out, status
+
+
 # ---------------------------------------------------------------------------------------------
 # delimited text ingest (SURVEY.md section 8f.3)
 # ---------------------------------------------------------------------------------------------

@@ -469,12 +469,15 @@ def tsqr_q(system, x_block, r_inv, entry, grid_shape):
 # ---------------------------------------------------------------------------------------------
 # Newton logistic regression
 # ---------------------------------------------------------------------------------------------
-def newton_lr(system, comm, x_blocks, y_blocks, d, tol, max_iter, grad_hess):
+def newton_lr(system, comm, x_blocks, y_blocks, d, tol, max_iter, grad_hess, step=None):
     """Newton iterations (glms.py:362-372) on row-sharded data; returns (beta, iterations).
 
     ``grad_hess(x_blocks, y_blocks, beta) -> 1-D buffer of d + d*d`` (summed over the blocks) is the
     fused kernel (cuda_compute.lr_grad_hess_blocks) or, in the CPU tests, its NumPy statement.  The all-reduce of that
     buffer replaces the reference's gathers (``sum_reduce`` of G gradients, the (d, d) add chain).
+    ``step(gh, beta) -> (new beta, status)`` optionally fuses the update itself (cuda_compute.newton_step:
+    solve, subtract, max |g| and the singularity flag in one launch, one 16-byte read-back per iteration);
+    without it the update runs through the kernel interface like the reference (inv, tensordot, sub, abs, max).
     """
     beta = system.new_block("zeros", (0,), {"shape": (d,), "block_shape": (d,), "dtype": "float64"},
                             syskwargs={"grid_entry": (0,), "grid_shape": (1,)})
@@ -484,11 +487,19 @@ def newton_lr(system, comm, x_blocks, y_blocks, d, tol, max_iter, grad_hess):
         iters += 1
         acc = grad_hess(x_blocks, y_blocks, beta)    # g | H summed over this rank's row blocks
         comm.all_reduce_sum(acc)
+        if step is not None:
+            beta, status = step(acc, beta)
+            gmax, info = (float(v) for v in np.asarray(system.get(status)))     # the one host sync per iteration
+            if info != 0:
+                raise np.linalg.LinAlgError("Singular matrix")
+            if gmax <= tol:
+                break
+            continue
         g = acc[:d]
         h = acc[d:].reshape(d, d) if isinstance(acc, np.ndarray) else acc[d:].view(d, d)
         h_inv = system.inv(h, syskwargs={"grid_entry": (0, 0), "grid_shape": (1, 1)})
-        step = system.bop("tensordot", h_inv, g, (d, d), (d,), False, False, axes=1, syskwargs=sk)
-        beta = system.bop("sub", beta, step, (d,), (d,), False, False, axes=None, syskwargs=sk)
+        step_vec = system.bop("tensordot", h_inv, g, (d, d), (d,), False, False, axes=1, syskwargs=sk)
+        beta = system.bop("sub", beta, step_vec, (d,), (d,), False, False, axes=None, syskwargs=sk)
         gmax = system.reduce_axis("max", system.map_uop("abs", g, (), {}, syskwargs=sk), None, False, False, syskwargs=sk)
         if float(np.asarray(system.get(gmax))) <= tol:     # the one host sync per iteration
             break

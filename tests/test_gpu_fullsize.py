@@ -145,6 +145,11 @@ def test_config4_newton_full_size_properties(cuda_system):
     # Newton to convergence, then stationarity
     beta, iters = multi_gpu.newton_lr(cuda_system, multi_gpu.Comm(), xs, ys, d, 1e-6, 25, cc.lr_grad_hess_blocks)
     assert iters < 25
+    # the fused update kernel takes the same path: same iteration count, same beta to rounding
+    beta_f, iters_f = multi_gpu.newton_lr(cuda_system, multi_gpu.Comm(), xs, ys, d, 1e-6, 25, cc.lr_grad_hess_blocks,
+                                          step=cc.newton_step)
+    assert iters_f == iters
+    assert np.linalg.norm(cuda_system.get(beta_f) - cuda_system.get(beta)) <= 1e-10 * np.linalg.norm(cuda_system.get(beta))
     final = cuda_system.get(cc.lr_grad_hess_blocks(xs, ys, beta))
     assert np.abs(final[:d]).max() <= 1e-6
     b = cuda_system.get(beta)

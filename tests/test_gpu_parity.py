@@ -696,3 +696,28 @@ def test_lr_grad_hess_blocks(cuda_system):
                                                                [cuda_system.put(v) for v in ys], cuda_system.put(beta)))
         assert rel_fro(out[:d], g) <= GEMM_TOL
         assert rel_fro(out[d:].reshape(d, d), H) <= GEMM_TOL
+
+
+@pytest.mark.parametrize("d", [1, 5, 28, 64, 128])
+def test_newton_step(cuda_system, d):
+    """nums_newton_step against the reference's update (glms.py:362-372): beta - inv(H) @ g, max |g|."""
+    from nums_b200 import cuda_compute as cc
+    rng = np.random.default_rng(70 + d)
+    A = rng.standard_normal((3 * d + 2, d))
+    H = A.T @ A
+    if d > 1:
+        H[[0, d - 1]] = H[[d - 1, 0]]            # not symmetric any more: forces row exchanges
+    g = rng.standard_normal(d)
+    beta = rng.standard_normal(d)
+    out, status = cc.newton_step(cuda_system.put(np.concatenate([g, H.ravel()])), cuda_system.put(beta))
+    want = beta - np.linalg.inv(H) @ g
+    assert rel_fro(cuda_system.get(out), want) <= 1e-10
+    gmax, info = cuda_system.get(status)
+    assert gmax == np.max(np.abs(g)) and info == 0
+    singular = H.copy()
+    singular[:, 0] = 0.0
+    _out, status = cc.newton_step(cuda_system.put(np.concatenate([g, singular.ravel()])), cuda_system.put(beta))
+    assert cuda_system.get(status)[1] == 1
+    g[d // 2] = np.nan
+    _out, status = cc.newton_step(cuda_system.put(np.concatenate([g, H.ravel()])), cuda_system.put(beta))
+    assert np.isnan(cuda_system.get(status)[0])

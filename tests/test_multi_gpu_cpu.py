@@ -33,6 +33,12 @@ def _np_grad_hess(X, y, beta):
     return np.concatenate([g, H.reshape(-1)])
 
 
+def _np_newton_step(gh, beta):
+    d = beta.shape[0]
+    g, H = gh[:d], gh[d:].reshape(d, d)
+    return beta - np.linalg.solve(H, g), np.array([np.max(np.abs(g)), 0.0])
+
+
 def _worker(rank, world, port, results):
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     try:
@@ -70,6 +76,9 @@ def _worker(rank, world, port, results):
         ys = [yl[i * 50:(i + 1) * 50] for i in range(8) if i % world == rank]
         beta, iters = multi_gpu.newton_lr(system, comm, xs, ys, 5, 1e-10, 6, _np_grad_hess_blocks)
         out["beta"], out["iters"] = np.asarray(beta), iters
+        # the same iteration with the update fused into one `step` call (NumPy statement of newton_step)
+        beta_f, iters_f = multi_gpu.newton_lr(system, comm, xs, ys, 5, 1e-10, 6, _np_grad_hess_blocks, step=_np_newton_step)
+        assert iters_f == iters and np.allclose(np.asarray(beta_f), np.asarray(beta), rtol=1e-12, atol=1e-14)
         results[rank] = out
     finally:
         dist.destroy_process_group()
