@@ -123,6 +123,16 @@ int nums_bop(int op, int loop_dtype, const nums_array_t* a, const nums_array_t* 
 int nums_uop(int op, int loop_dtype, const nums_array_t* a, const nums_array_t* out,
              void* stream);
 
+/* Batched element / slice scatter: for every pair p, dst[o][dst_index[p]][i] = src[o][src_index[p]][i]
+ * over dense (outer, dst_len, inner) / (outer, src_len, inner) views of elem_size-byte elements
+ * (1, 4 or 8).  One launch for the per-pair loops of update_block_by_index (flattened arrays,
+ * outer = inner = 1) and update_block_along_axis (numpy_compute.py:154-169).  Indices are device
+ * int64, already normalised and free of duplicate destinations (the caller keeps the last pair,
+ * which is what the reference's sequential loop leaves behind). */
+int nums_scatter_axis(int elem_size, int64_t outer, int64_t dst_len, int64_t src_len, int64_t inner,
+                      int64_t npairs, const int64_t* dst_index, const int64_t* src_index, void* dst,
+                      const void* src, void* stream);
+
 /* out = sum of n same-shape contiguous arrays, left to right (np.add.reduce(arrs),
  * numpy_compute.py:210-211).  `arrs_host` is a HOST array of n device pointers. */
 int nums_sum_reduce(int n, const void* const* arrs_host, int dtype, int64_t numel, void* out,

@@ -160,6 +160,7 @@ class _Lib(object):
             "nums_cholesky": ([I, L, P, L, P, L, P, P, Z, P], I),
             "nums_gram_factor": ([L, P, L, P, L, P, L, P, L, P, P], I),
             "nums_newton_step": ([L, P, P, P, P, P], I),
+            "nums_scatter_axis": ([I, L, L, L, L, L, P, P, P, P, P], I),
             "nums_csv_index": ([P, L, L, I, P, P, Z, P], I),
             "nums_csv_parse": ([P, L, L, I, I, L, L, P, P, P, P], I),
             "nums_svd": ([I, L, P, L, P, P, P, P, Z, P], I),
@@ -174,7 +175,7 @@ class _Lib(object):
     EXPORTS = ("nums_abi_version nums_last_error nums_last_workspace_request nums_sm_count nums_launch_count nums_bop "
                "nums_uop nums_sum_reduce nums_fill nums_arange nums_eye nums_reduce nums_arg_op "
                "nums_allclose nums_nonzero_count nums_nonzero_fill nums_gemm nums_gemm_grouped nums_qr nums_inv "
-               "nums_cholesky nums_gram_factor nums_svd nums_lr_grad_hess nums_lr_grad_hess_blocks nums_newton_step nums_csv_index "
+               "nums_cholesky nums_gram_factor nums_svd nums_lr_grad_hess nums_lr_grad_hess_blocks nums_newton_step nums_scatter_axis nums_csv_index "
                "nums_csv_parse").split()
 
     # -- error handling ---------------------------------------------------------------------

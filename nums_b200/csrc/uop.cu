@@ -247,6 +247,25 @@ int by_storage(int dtype, F&& f) {
   NUMS_FAIL(NUMS_ERR_INVALID, "unknown dtype %d", dtype);
 }
 
+// dst[o][dst_index[p]][i] = src[o][src_index[p]][i] for every pair p: the per-pair loops of
+// update_block_by_index / update_block_along_axis (numpy_compute.py:154-169) as ONE launch.  Both
+// arrays are dense (outer, length, inner) views of the same element size; the caller removed
+// duplicate destinations (last pair wins, as in the reference's sequential loop), so pairs are
+// independent.  W = element width in bytes (1, 4, 8): the copy is bitwise.
+template <typename W>
+__global__ void __launch_bounds__(256)
+scatter_axis_kernel(W* __restrict__ dst, const W* __restrict__ src, const int64_t* __restrict__ dst_index,
+                    const int64_t* __restrict__ src_index, int64_t outer, int64_t dst_len, int64_t src_len,
+                    int64_t inner, int64_t npairs) {
+  const int64_t total = outer * npairs * inner;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e % inner;
+    const int64_t p = (e / inner) % npairs;
+    const int64_t o = e / (inner * npairs);
+    dst[(o * dst_len + dst_index[p]) * inner + i] = src[(o * src_len + src_index[p]) * inner + i];
+  }
+}
+
 }  // namespace
 }  // namespace nums
 
@@ -389,4 +408,34 @@ extern "C" int nums_eye(const nums_array_t* out, void* stream) {
     NUMS_LAUNCH_OK();
     return NUMS_OK;
   });
+}
+
+extern "C" int nums_scatter_axis(int elem_size, int64_t outer, int64_t dst_len, int64_t src_len, int64_t inner,
+                                 int64_t npairs, const int64_t* dst_index, const int64_t* src_index, void* dst,
+                                 const void* src, void* stream) {
+  using namespace nums;
+  NUMS_REQUIRE(outer >= 0 && dst_len >= 0 && src_len >= 0 && inner >= 0 && npairs >= 0, "scatter_axis: negative extent");
+  const int64_t total = outer * npairs * inner;
+  if (total == 0) return NUMS_OK;
+  NUMS_REQUIRE(dst && src && dst_index && src_index, "scatter_axis: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = blocks_for(total, 256, (int64_t)sm_count() * 16);
+  switch (elem_size) {
+    case 1:
+      scatter_axis_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<uint8_t*>(dst), static_cast<const uint8_t*>(src), dst_index,
+                                                        src_index, outer, dst_len, src_len, inner, npairs);
+      break;
+    case 4:
+      scatter_axis_kernel<uint32_t><<<grid, 256, 0, s>>>(static_cast<uint32_t*>(dst), static_cast<const uint32_t*>(src),
+                                                         dst_index, src_index, outer, dst_len, src_len, inner, npairs);
+      break;
+    case 8:
+      scatter_axis_kernel<uint64_t><<<grid, 256, 0, s>>>(static_cast<uint64_t*>(dst), static_cast<const uint64_t*>(src),
+                                                         dst_index, src_index, outer, dst_len, src_len, inner, npairs);
+      break;
+    default:
+      NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "scatter_axis: element size %d", elem_size);
+  }
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
 }

@@ -225,6 +225,42 @@ def _materialize(view, dtype=None):
     return out
 
 
+def _ravel_indices(indices, shape):
+    """Multi-indices (NumPy semantics: negative values wrap, out of range raises IndexError) -> int64
+    offsets into a C-ordered array of `shape`."""
+    idx = np.asarray(indices, dtype=np.int64).reshape(len(indices), len(shape))
+    dims = np.asarray(shape, dtype=np.int64)
+    if np.any(idx < -dims) or np.any(idx >= dims):
+        bad = idx[np.any((idx < -dims) | (idx >= dims), axis=1)][0]
+        raise IndexError("index %s is out of bounds for shape %s" % (tuple(int(v) for v in bad), tuple(shape)))
+    idx = np.where(idx < 0, idx + dims, idx)
+    strides = np.ones(len(shape), dtype=np.int64)
+    for k in range(len(shape) - 2, -1, -1):
+        strides[k] = strides[k + 1] * dims[k + 1]
+    return idx @ strides
+
+
+def _scatter(dst, src, dst_index, src_index, outer, dst_len, src_len, inner):
+    """dst[o, dst_index[p], i] = src[o, src_index[p], i] in one launch (nums_scatter_axis).  `dst` is a
+    dense array this call may write; duplicate destinations keep their LAST pair, like the sequential
+    loops of the reference (numpy_compute.py:154-169)."""
+    if src.dtype != dst.dtype or not src.is_contiguous():
+        src = _materialize(src, dst.dtype)            # ndarray assignment casts to the destination dtype
+    dst_index = np.asarray(dst_index, dtype=np.int64)
+    src_index = np.asarray(src_index, dtype=np.int64)
+    if np.unique(dst_index).size != dst_index.size:
+        last = {}
+        for pos, d in enumerate(dst_index.tolist()):
+            last[d] = pos
+        keep = np.fromiter(sorted(last.values()), dtype=np.int64)
+        dst_index, src_index = dst_index[keep], src_index[keep]
+    both = upload(np.concatenate([dst_index, src_index]))
+    n = int(dst_index.size)
+    LIB.check(LIB.dll.nums_scatter_axis(dst.element_size(), int(outer), int(dst_len), int(src_len), int(inner), n,
+                                        both.data_ptr(), both.data_ptr() + 8 * n, dst.data_ptr(), src.data_ptr(),
+                                        _stream()))
+
+
 def _transpose_view(t):
     return t.permute(*reversed(range(t.dim()))) if t.dim() > 1 else t
 
@@ -429,15 +465,32 @@ class ComputeCls(_ComputeImp):
     def update_block_by_index(self, dst_arr, src_arr, index_pairs):
         result = _materialize(upload(dst_arr))
         src = upload(src_arr)
-        for dst_index, src_index in index_pairs:
-            _copy_into(result[tuple(int(i) for i in dst_index)], src[tuple(int(i) for i in src_index)])
+        pairs = list(index_pairs)
+        if not pairs:
+            return result
+        dst_lin = _ravel_indices([p[0] for p in pairs], tuple(result.shape))
+        src_lin = _ravel_indices([p[1] for p in pairs], tuple(src.shape))
+        _scatter(result, src, dst_lin, src_lin, 1, result.numel(), src.numel(), 1)
         return result
 
     def update_block_along_axis(self, dst_arr, src_arr, index_pairs, axis):
         result = _materialize(upload(dst_arr))
         src = upload(src_arr)
-        for dst_index, src_index in index_pairs:
-            _copy_into(result.select(axis, int(dst_index)), src.select(axis, int(src_index)))
+        pairs = list(index_pairs)
+        if not pairs:
+            return result
+        axis = int(axis) % result.dim()
+        other = tuple(result.shape[:axis]) + tuple(result.shape[axis + 1:])
+        if src.dim() != result.dim() or other != tuple(src.shape[:axis]) + tuple(src.shape[axis + 1:]):
+            # shapes that only agree through broadcasting: pair by pair with the broadcasting copy kernel
+            for dst_index, src_index in pairs:
+                _copy_into(result.select(axis, int(dst_index)), src.select(axis, int(src_index)))
+            return result
+        dst_idx = _ravel_indices([(p[0],) for p in pairs], (result.shape[axis],))
+        src_idx = _ravel_indices([(p[1],) for p in pairs], (src.shape[axis],))
+        outer = int(np.prod(result.shape[:axis], dtype=np.int64))
+        inner = int(np.prod(result.shape[axis + 1:], dtype=np.int64))
+        _scatter(result, src, dst_idx, src_idx, outer, result.shape[axis], src.shape[axis], inner)
         return result
 
     def transpose(self, arr):

@@ -721,3 +721,40 @@ def test_newton_step(cuda_system, d):
     g[d // 2] = np.nan
     _out, status = cc.newton_step(cuda_system.put(np.concatenate([g, H.ravel()])), cuda_system.put(beta))
     assert np.isnan(cuda_system.get(status)[0])
+
+
+def test_batched_scatter_kernels(cuda_system, oracle):
+    """update_block_by_index / update_block_along_axis as one launch (nums_scatter_axis): many pairs,
+    duplicate destinations (the last pair wins), negative indices, 1-D to 3-D, every dtype, dtype-casting
+    assignment, and NumPy's IndexError."""
+    rng = np.random.default_rng(71)
+    for dt in (np.float64, np.float32, np.int64, np.int32, np.bool_):
+        dst = (rng.standard_normal((37, 23)) * 100).astype(dt)
+        src = (rng.standard_normal((41, 19)) * 100).astype(dt)
+        pairs = [((int(rng.integers(-37, 37)), int(rng.integers(-23, 23))), (int(rng.integers(-41, 41)), int(rng.integers(-19, 19))))
+                 for _ in range(900)]                     # 851 cells -> plenty of duplicate destinations
+        got = cuda_system.get(cuda_system.update_block_by_index(cuda_system.put(dst), cuda_system.put(src), pairs, syskwargs={}))
+        assert_exact(got, oracle.update_block_by_index(dst, src, pairs))
+    # permutation of a vector (nums.numpy.random.permutation / shuffle, test_np_random.py:46-106)
+    v = rng.standard_normal(5000)
+    perm = rng.permutation(5000)
+    pairs = [((int(i),), (int(j),)) for i, j in enumerate(perm)]
+    got = cuda_system.get(cuda_system.update_block_by_index(cuda_system.put(np.zeros(5000)), cuda_system.put(v), pairs, syskwargs={}))
+    assert_exact(got, v[perm])
+    # slices along each axis of a 3-D block, duplicates and negative indices included
+    dst3 = rng.standard_normal((7, 9, 5))
+    for axis, n_dst, n_src in ((0, 7, 11), (1, 9, 4), (2, 5, 6)):
+        shape = list(dst3.shape)
+        shape[axis] = n_src
+        src3 = rng.standard_normal(shape)
+        pairs = [(int(rng.integers(-n_dst, n_dst)), int(rng.integers(-n_src, n_src))) for _ in range(20)]
+        got = cuda_system.get(cuda_system.update_block_along_axis(cuda_system.put(dst3), cuda_system.put(src3), pairs, axis,
+                                                                  syskwargs={}))
+        assert_exact(got, oracle.update_block_along_axis(dst3, src3, pairs, axis))
+    # assignment casts to the destination dtype
+    di, sf = np.arange(12, dtype=np.int64).reshape(3, 4), rng.standard_normal((3, 4)) * 10
+    pairs = [((0, 0), (2, 3)), ((2, 1), (0, 0))]
+    got = cuda_system.get(cuda_system.update_block_by_index(cuda_system.put(di), cuda_system.put(sf), pairs, syskwargs={}))
+    assert_exact(got, oracle.update_block_by_index(di, sf, pairs))
+    with pytest.raises(IndexError):
+        cuda_system.update_block_by_index(cuda_system.put(di), cuda_system.put(sf), [((3, 0), (0, 0))], syskwargs={})
