@@ -1057,6 +1057,37 @@ def _find_byte(view, value, start):
     return -1
 
 
+_READ_CHUNK = 8 << 20
+_read_pool = None
+
+
+def _read_range(fd, offset, target, filename):
+    """Fill the writable buffer `target` with the bytes of file `fd` starting at `offset`.  Large ranges
+    are read by a few threads with positional reads (the page-cache copy runs outside the GIL): a
+    single `readinto` of page-locked memory was the largest part of an end-to-end CSV ingest."""
+    import os
+    total = len(target)
+
+    def fill(lo, hi):
+        pos = lo
+        while pos < hi:
+            got = os.preadv(fd, [target[pos:hi]], offset + pos)
+            if got <= 0:
+                raise IOError("short read from %s" % filename)
+            pos += got
+
+    if total <= _READ_CHUNK:
+        fill(0, total)
+        return
+    global _read_pool
+    if _read_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _read_pool = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1), thread_name_prefix="nums-csv-read")
+    jobs = [_read_pool.submit(fill, lo, min(total, lo + _READ_CHUNK)) for lo in range(0, total, _READ_CHUNK)]
+    for job in jobs:
+        job.result()
+
+
 def read_csv_block(filename, file_start, file_end, dtype, delimiter, has_header):
     """``read_csv_block`` of the reference (filesystem.py:157-212) with the parsing on the device.
 
@@ -1083,10 +1114,7 @@ def read_csv_block(filename, file_start, file_end, dtype, delimiter, has_header)
             want = min(size, file_end + slack) - file_start
             pinned = torch.empty(((want + 63) // 32 * 32,), dtype=torch.uint8, pin_memory=True)
             view = pinned.numpy()
-            fh.seek(file_start)
-            got = fh.readinto(memoryview(view)[:want])
-            if got != want:
-                raise IOError("short read from %s" % filename)
+            _read_range(fh.fileno(), file_start, memoryview(view)[:want], filename)
             view[want:] = 0
             # the last line of the chunk is the one holding byte file_end - 1; it ends at its newline
             last_nl = _find_byte(view[:want], 10, file_end - 1 - file_start)

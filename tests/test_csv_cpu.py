@@ -91,3 +91,19 @@ def test_filesystem_read_csv_mirror_over_oracle(tmp_path):
     assert got.shape[0] == x.shape[0] - len(dropped)
     if not dropped:
         assert np.array_equal(got, x)
+
+
+def test_read_range_parallel_positional_reads(tmp_path):
+    """The host-side file reader of read_csv_block: multi-chunk ranges are read by a thread pool with
+    positional reads; content, offsets and the short-read error."""
+    from nums_b200 import cuda_compute as cc
+    data = np.random.default_rng(8).integers(0, 256, 20_000_003, dtype=np.uint8)
+    path = str(tmp_path / "blob.bin")
+    data.tofile(path)
+    with open(path, "rb") as fh:
+        for offset, count in ((0, data.size), (12345, 17_000_000), (data.size - 1003, 1003), (7, 5), (3, 0)):
+            buf = np.zeros(count, dtype=np.uint8)
+            cc._read_range(fh.fileno(), offset, memoryview(buf), path)
+            assert np.array_equal(buf, data[offset:offset + count])
+        with pytest.raises(IOError):
+            cc._read_range(fh.fileno(), data.size - 10, memoryview(np.zeros(11, dtype=np.uint8)), path)
