@@ -46,6 +46,33 @@ def _dmma_ok(t, ld):
     return t.dtype == torch.float64 and t.data_ptr() % 16 == 0 and ld % 2 == 0
 
 
+def plan_launch_groups(needs, done, max_groups):
+    """Pure planning step of ``ContractionQueue._launch_groups``.
+
+    ``needs[i]`` is ``None`` or ``(sequence number, event)`` of the latest upload contraction i reads;
+    uploads up to sequence number ``done`` have already been waited for.  Returns a list of
+    ``(indices, upto)``: contractions that become ready together form a run, runs are ordered by
+    readiness and neighbouring runs merged until at most ``max_groups`` launches remain; ``upto`` is
+    the latest upload the launch has to wait for (``None``: nothing)."""
+    if all(n is None or n[0] <= done for n in needs):
+        return [(list(range(len(needs))), None)]
+    seq_of = [n[0] if n is not None and n[0] > done else 0 for n in needs]
+    order = sorted(range(len(needs)), key=lambda i: seq_of[i])     # stable: creation order inside a run
+    runs = []
+    for i in order:
+        if runs and seq_of[runs[-1][-1]] == seq_of[i]:
+            runs[-1].append(i)
+        else:
+            runs.append([i])
+    merge = max(1, -(-len(runs) // max_groups))
+    out = []
+    for lo in range(0, len(runs), merge):
+        idx = [i for run in runs[lo:lo + merge] for i in run]
+        tags = [needs[i] for i in idx if seq_of[i]]
+        out.append((idx, max(tags, key=lambda t: t[0]) if tags else None))
+    return out
+
+
 class ContractionQueue(object):
 
     def __init__(self):
@@ -148,30 +175,11 @@ class ContractionQueue(object):
         Operands uploaded asynchronously (cuda_compute.upload) carry their upload's sequence number;
         contractions are ordered by the latest upload they read and cut into at most MAX_GROUPS
         launches (one per set of contractions that become ready together), each waiting only for what
-        it reads, so the GEMM overlaps the rest of the H2D
-        traffic.  With nothing in flight this is a single launch."""
-        stream_key = cuda_compute._stream_unordered()
-        done = cuda_compute._Transfers.awaited.get(stream_key, 0)
+        it reads, so the GEMM overlaps the rest of the H2D traffic.  With nothing in flight this is a
+        single launch."""
+        done = cuda_compute._Transfers.awaited.get(cuda_compute._stream_unordered(), 0)
         needs = [self._need(d) for d in group]
-        if all(n is None or n[0] <= done for n in needs):
-            return [(group, None)]
-        seq_of = [n[0] if n is not None and n[0] > done else 0 for n in needs]
-        order = sorted(range(len(group)), key=lambda i: seq_of[i])
-        # runs of contractions that become ready together; neighbouring runs are merged until at most
-        # MAX_GROUPS launches remain
-        runs = []
-        for i in order:
-            if runs and seq_of[runs[-1][-1]] == seq_of[i]:
-                runs[-1].append(i)
-            else:
-                runs.append([i])
-        merge = max(1, -(-len(runs) // MAX_GROUPS))
-        out = []
-        for lo in range(0, len(runs), merge):
-            idx = [i for run in runs[lo:lo + merge] for i in run]
-            tags = [needs[i] for i in idx if seq_of[i]]
-            out.append(([group[i] for i in idx], max(tags, key=lambda t: t[0]) if tags else None))
-        return out
+        return [([group[i] for i in idx], upto) for idx, upto in plan_launch_groups(needs, done, MAX_GROUPS)]
 
     def _launch(self, ta, tb, group, upto, mark_done):
         if upto is not None:
