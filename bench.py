@@ -756,6 +756,18 @@ def run_gpu(args):
             workloads = other_workloads(system, quick=args.quick)
     else:
         workloads = sharded
+        try:    # per-GPU rate of the whole product (both grouped launches + whatever transfer time is exposed)
+            sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+            peak = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * (256 / 16.0) * 2 * sm_mhz * 1e6 / 1e12
+            roofline = {"bound": "tensor",
+                        "kernel": "dgemm_dmma_tma_kernel, the grouped launches of one SUMMA product on each rank",
+                        "achieved": value / world, "peak": peak, "unit": "TFLOP/s", "frac": value / world / peak,
+                        "scope": "per GPU over the whole timed step (max over ranks), not a kernel in isolation",
+                        "peak_source": "FP64 tensor-pipe issue limit = SMs x 4 sub-partitions x 256 FMA per 16 cycles x the SM clock "
+                                       "sampled on rank 0 (%.0f MHz)" % sm_mhz,
+                        "algorithmic_flops_per_launch": FLOPS_PER_STEP / world, "traffic": None}
+        except Exception:  # noqa: BLE001 -- reporting only
+            roofline = None
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
