@@ -527,14 +527,60 @@ class FileSystem(object):
     ``num_workers`` byte ranges (``Batch.from_num_batches``, storage/utils.py:30-62), every range goes
     to the registered ``read_csv_block`` kernel (one call per range, ``num_returns = 2``), and each
     non-empty result becomes a single-block ``BlockArray``.  ``read_csv_block`` defaults to the device
-    parser (``cuda_compute.read_csv_block``); the CPU tests pass the oracle's."""
+    parser (``cuda_compute.read_csv_block``); the CPU tests pass the oracle's.  Also mirrors the array
+    persistence calls (``write_fs`` / ``read_fs`` / ``delete_fs``) in the reference's on-disk format."""
 
-    def __init__(self, system, read_csv_block=None):
+    def __init__(self, system, read_csv_block=None, block_io=None):
         self.system = system
-        if read_csv_block is None:
+        if read_csv_block is None or block_io is None:
             from nums_b200 import cuda_compute
-            read_csv_block = cuda_compute.read_csv_block
+            read_csv_block = read_csv_block or cuda_compute.read_csv_block
+            block_io = block_io or (cuda_compute.write_block_fs, cuda_compute.read_block_fs, cuda_compute.delete_block_fs)
         self.system.register("read_csv_block", read_csv_block, {})
+        for name, func in zip(("write_block_fs", "read_block_fs", "delete_block_fs"), block_io):
+            self.system.register(name, func, {})
+
+    # -- array persistence: ArrayApplication.write_fs / read_fs / delete_fs (application.py:154-191,204-219) over
+    #    the block functions above and the meta file of filesystem.py:66-93,308-343 --------------------------
+    @staticmethod
+    def _meta_path(filename):
+        import os
+        os.makedirs(filename, exist_ok=True)
+        return os.path.join(filename, "meta.pkl")
+
+    def write_fs(self, ba, filename):
+        import pickle
+        for entry in ba.grid.get_entry_iterator():
+            self.system.call("write_block_fs", ba.blocks[entry].oid, filename, entry,
+                             syskwargs={"grid_entry": entry, "grid_shape": ba.grid.grid_shape})
+        meta = {"filename": filename, "grid_meta": ba.grid.to_meta(),
+                "addresses": self.system.get_block_addresses(ba.grid)}
+        with open(self._meta_path(filename), "wb") as fh:
+            pickle.dump(meta, fh)
+        return meta
+
+    def read_meta_fs(self, filename):
+        import pickle
+        with open(self._meta_path(filename), "rb") as fh:
+            return pickle.load(fh)
+
+    def read_fs(self, filename):
+        meta = self.read_meta_fs(filename)
+        grid = ArrayGrid.from_meta(meta["grid_meta"])
+        ba = BlockArray(grid, self.system)
+        for entry in meta["addresses"]:
+            ba.blocks[entry].oid = self.system.call("read_block_fs", filename, entry,
+                                                    syskwargs={"grid_entry": entry, "grid_shape": grid.grid_shape})
+        return ba
+
+    def delete_fs(self, filename):
+        import os
+        meta = self.read_meta_fs(filename)
+        grid = ArrayGrid.from_meta(meta["grid_meta"])
+        for entry in meta["addresses"]:
+            self.system.call("delete_block_fs", filename, entry,
+                             syskwargs={"grid_entry": entry, "grid_shape": grid.grid_shape})
+        os.remove(self._meta_path(filename))
 
     @staticmethod
     def byte_ranges(total_size, num_batches):

@@ -1167,3 +1167,37 @@ def parse_csv_text(text, first, stop, delimiter, dtype, cols):
         exc.offset = None if where >= (1 << 62) else where
         raise exc
     return out, (rows, cols)
+
+
+# ---------------------------------------------------------------------------------------------
+# block persistence (the reference's on-disk array format, used as checkpoint format)
+# ---------------------------------------------------------------------------------------------
+def _block_path(filename, grid_entry):
+    """<filename>/<i>_<j>...pkl -- the reference's layout (filesystem.py:63,111-129)."""
+    import os
+    os.makedirs(filename, exist_ok=True)
+    return os.path.join(filename, "_".join(str(int(i)) for i in grid_entry) + ".pkl")
+
+
+def write_block_fs(block, filename, grid_entry):
+    """``write_block_fs`` (filesystem.py:111-119): the block is downloaded and pickled as the same NumPy
+    array the reference would have written, so either side can read the other's files."""
+    import pickle
+    arr = download(upload(block))
+    with open(_block_path(filename, grid_entry), "wb") as fh:
+        pickle.dump(np.ascontiguousarray(arr), fh)
+    return None
+
+
+def read_block_fs(filename, grid_entry):
+    """``read_block_fs`` (filesystem.py:121-129): unpickle and upload."""
+    import pickle
+    with open(_block_path(filename, grid_entry), "rb") as fh:
+        return upload(np.asarray(pickle.load(fh)))
+
+
+def delete_block_fs(filename, grid_entry):
+    """``delete_block_fs`` (filesystem.py:131-139)."""
+    import os
+    os.remove(_block_path(filename, grid_entry))
+    return None

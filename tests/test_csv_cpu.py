@@ -107,3 +107,46 @@ def test_read_range_parallel_positional_reads(tmp_path):
             assert np.array_equal(buf, data[offset:offset + count])
         with pytest.raises(IOError):
             cc._read_range(fh.fileno(), data.size - 10, memoryview(np.zeros(11, dtype=np.uint8)), path)
+
+
+def test_block_persistence_reference_format(tmp_path):
+    """write_fs / read_fs mirror (application.py:154-191) over the CPU oracle system: round trip, the
+    reference's directory layout, and -- with the reference tree mounted -- files written by either side
+    are read by the other."""
+    import pickle
+    from nums_b200 import blocks
+    from oracle import csv_oracle, ref_loader
+    from tests.helpers import OracleSystem
+
+    def np_write(block, filename, entry):
+        os.makedirs(filename, exist_ok=True)
+        with open(os.path.join(filename, "_".join(map(str, entry)) + ".pkl"), "wb") as fh:
+            pickle.dump(np.asarray(block), fh)
+
+    def np_read(filename, entry):
+        with open(os.path.join(filename, "_".join(map(str, entry)) + ".pkl"), "rb") as fh:
+            return pickle.load(fh)
+
+    def np_delete(filename, entry):
+        os.remove(os.path.join(filename, "_".join(map(str, entry)) + ".pkl"))
+
+    system = OracleSystem()
+    fs = blocks.FileSystem(system, csv_oracle.read_csv_block, (np_write, np_read, np_delete))
+    app = blocks.ArrayApp(system)
+    x = np.random.default_rng(11).standard_normal((37, 21))
+    X = app.array(x, (16, 8))
+    target = str(tmp_path / "arr")
+    meta = fs.write_fs(X, target)
+    assert sorted(os.listdir(target)) == sorted(["meta.pkl"] + ["%d_%d.pkl" % e for e in X.grid.get_entry_iterator()])
+    assert meta["grid_meta"] == {"shape": (37, 21), "block_shape": (16, 8), "dtype": "float64"}
+    back = fs.read_fs(target)
+    assert back.grid.to_meta() == X.grid.to_meta() and np.array_equal(back.get(), x)
+    if ref_loader.available():
+        ref_loader.load()
+        from nums.core.systems import filesystem as ref_fs
+        assert np.array_equal(ref_fs.read_block_fs(target, (1, 2)), x[16:32, 16:21])          # reference reads our files
+        ref_fs.write_block_fs(x[:16, :8] * 2.0, target, (0, 0))                                 # we read the reference's
+        assert np.array_equal(fs.read_fs(target).get()[:16, :8], x[:16, :8] * 2.0)
+        assert ref_fs.read_meta_fs(target)["grid_meta"] == meta["grid_meta"]
+    fs.delete_fs(target)
+    assert os.listdir(target) == []
