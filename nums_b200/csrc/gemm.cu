@@ -2,12 +2,16 @@
 // nums/core/systems/numpy_compute.py:231-232 (OpenBLAS dgemm/dgemv in the reference).
 //
 //   * f64 GEMM: FP64 tensor pipe.  On sm_100a every mma.sync f64 shape lowers to DMMA.8x8x4
-//     (checked with cuobjdump), so the kernel is written directly against m8n8k4 fragments:
-//     128x128x32 CTA tiles, 8 warps of 32x64, a 3-stage cp.async shared-memory ring padded so
-//     that every fragment read is bank-conflict free, optional split-K for small outputs with
-//     long contractions (X^T X, the LR Hessian).  Operands may be stored transposed
-//     (BlockArray.T is lazy, base.py:72-85), handled by the shared-memory layout, not by a
-//     copy.
+//     (checked with cuobjdump), so the kernels are written directly against m8n8k4 fragments:
+//     128x128x32 CTA tiles, 8 MMA warps of 32x64, a 3-stage shared-memory ring padded so that
+//     every fragment read is bank-conflict free, optional split-K for small outputs with long
+//     contractions (X^T X, the LR Hessian), grouped launches over many output blocks whose
+//     tiles accumulate a whole k-chain of terms in registers.  Operands may be stored
+//     transposed (BlockArray.T is lazy, base.py:72-85), handled by the shared-memory layout,
+//     not by a copy.  Two feeds for the same tile code: dgemm_dmma_tma_kernel (default: a
+//     producer warp issues two tensor-map TMA copies per k-tile, mbarrier hand-off, 36.3 TFLOP/s)
+//     and dgemm_dmma_kernel (cp.async issued by the MMA warps, 33.4 TFLOP/s; the fallback when
+//     cuTensorMapEncodeTiled is unavailable, and NUMS_GEMM_FEED=cpasync for comparisons).
 //   * matrix-vector / vector-vector forms (BlockArray._matvec / _vecdot, blockarray.py:475-580):
 //     HBM-bound streaming kernels.
 //   * everything else (f32, exact integer tensordot from tests/core/array/test_bop.py:38-42,
