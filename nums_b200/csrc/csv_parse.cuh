@@ -55,6 +55,22 @@ static const Pow5 kPow5Host[kPow5High - kPow5Low + 1] = {
 #include "pow5_table.inc"
 };
 
+// exact powers of ten for Clinger's fast path (10^22 is the largest power of ten a double holds exactly)
+#define NUMS_POW10_LIST 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, \
+                        1e17, 1e18, 1e19, 1e20, 1e21, 1e22
+#if defined(__CUDACC__)
+static __device__ const double kPow10Device[23] = {NUMS_POW10_LIST};
+#endif
+static const double kPow10Host[23] = {NUMS_POW10_LIST};
+
+NUMS_HD double pow10_exact(int e) {
+#if defined(__CUDA_ARCH__)
+  return kPow10Device[e];
+#else
+  return kPow10Host[e];
+#endif
+}
+
 NUMS_HD Pow5 pow5(int q) {
 #if defined(__CUDA_ARCH__)
   return kPow5Device[q - kPow5Low];
@@ -238,10 +254,8 @@ NUMS_HD int parse_float(const uint8_t* p, int n, double* out) {
   const int q = (int)exp10;
   if (!truncated && w <= ((uint64_t)1 << 53) && q >= -22 && q <= 22) {
     // Clinger: both operands exact, one correctly rounded operation
-    const double p10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
-                            1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
     double d = (double)w;
-    d = q < 0 ? d / p10[-q] : d * p10[q];
+    d = q < 0 ? d / pow10_exact(-q) : d * pow10_exact(q);
     *out = negative ? -d : d;
     return FIELD_OK;
   }
