@@ -79,6 +79,13 @@ def dtype_code(dt):
     return code
 
 
+def supported_dtype(dt):
+    try:
+        return np.dtype(dt) in _NP_TO_CODE
+    except TypeError:
+        return False
+
+
 def torch_dtype(dt):
     if isinstance(dt, torch.dtype):
         return dt

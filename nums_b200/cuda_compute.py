@@ -1201,3 +1201,23 @@ def delete_block_fs(filename, grid_entry):
     import os
     os.remove(_block_path(filename, grid_entry))
     return None
+
+
+def loadtxt_block(fname, dtype, comments, delimiter, converters, skiprows, usecols, unpack, ndmin, encoding,
+                  max_rows):
+    """``loadtxt_block`` (filesystem.py:144-155): NumPy's text reader on the host (it is a general
+    tokenizer with comments / converters / usecols, i.e. I/O, not arithmetic), result uploaded."""
+    return upload(np.loadtxt(fname, dtype=dtype, comments=comments, delimiter=delimiter, converters=converters,
+                             skiprows=skiprows, usecols=usecols, unpack=unpack, ndmin=ndmin, encoding=encoding,
+                             max_rows=max_rows))
+
+
+# block-level I/O functions the reference's FileSystem registers (filesystem.py:224-231) for which this
+# module has device-aware versions; CudaSystem.register substitutes them by name.
+DEVICE_FUNCTIONS = {
+    "write_block_fs": write_block_fs,
+    "read_block_fs": read_block_fs,
+    "delete_block_fs": delete_block_fs,
+    "read_csv_block": read_csv_block,
+    "loadtxt_block": loadtxt_block,
+}

@@ -27,6 +27,26 @@ from nums_b200.deferred import ContractionQueue, DeferredContraction
 _BOP_PARAMS = ("op", "a1", "a2", "a1_shape", "a2_shape", "a1_T", "a2_T", "axes")
 
 
+def _host_function(func):
+    """Adapter for registered host-side (I/O) functions: device blocks in -> ndarrays, ndarray results
+    of a supported dtype -> device blocks."""
+    def to_host(v):
+        return cuda_compute.download(v) if isinstance(v, torch.Tensor) else v
+
+    def to_device(v):
+        if isinstance(v, np.ndarray) and v.dtype != object and cuda_compute._lib.supported_dtype(v.dtype):
+            return cuda_compute.upload(v)
+        if isinstance(v, tuple):
+            return tuple(to_device(x) for x in v)
+        return v
+
+    def wrapper(*args, **kwargs):
+        out = func(*[to_host(a) for a in args], **{k: to_host(v) for k, v in kwargs.items()})
+        return to_device(out)
+    wrapper.__name__ = getattr(func, "__name__", "host_function")
+    return wrapper
+
+
 class CudaSystem(object):
 
     def __init__(self, compute_module=cuda_compute, device=None, rank=0, world_size=1,
@@ -61,8 +81,9 @@ class CudaSystem(object):
             self.methods[name] = self._make_callable(name)
 
     def shutdown(self):
-        self.methods.clear()
-        self.remote_functions.clear()
+        # like SerialSystem.shutdown (systems.py:91-92) this leaves the system usable: the reference keeps
+        # module-level objects (e.g. the nums.numpy.random state) that outlive an application
+        self.contractions.flush()
 
     def _make_callable(self, name):
         def kernel(*args, **kwargs):
@@ -148,9 +169,15 @@ class CudaSystem(object):
         return function
 
     def register(self, name, func, remote_params=None):
+        """``System.register`` (systems.py:100-105).  The reference's ``FileSystem`` registers its
+        block-level I/O functions here (filesystem.py:224-231); those written against NumPy blocks are
+        replaced by the device-aware versions the compute module provides (``DEVICE_FUNCTIONS``:
+        block persistence and the CSV parser), everything else (metadata, S3, ``loadtxt_block``) runs
+        on the host with blocks downloaded on the way in and array results uploaded on the way out."""
         if name in self.remote_functions:
             return
-        self.remote_functions[name] = func
+        device_fn = getattr(self.compute_module, "DEVICE_FUNCTIONS", {}).get(name)
+        self.remote_functions[name] = device_fn if device_fn is not None else _host_function(func)
         self.methods[name] = self._make_callable(name)
 
     def nodes(self):

@@ -4,9 +4,10 @@ This module is part of ``oracle/``: only ``tests/``, ``oracle/make_golden.py``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` leg may import
 it.  Nothing under ``nums_b200/`` may.
 
-It imports the unmodified reference package from ``/root/reference`` (which
-exists only in the build container, never on the GPU box) under a small
-in-memory compatibility layer, because the reference pins ``numpy<=1.20`` and
+It imports the unmodified reference package from ``/root/reference`` (build
+container) or ``baseline/_ref`` (the pip --target install that travels to the GPU
+box, scripts/install_reference.sh) under a small in-memory compatibility layer
+(``nums_b200.reference_compat``), because the reference pins ``numpy<=1.20`` and
 ``ray<1.1`` (``setup.py:20-25``) while this image ships numpy 2.3 and no ray /
 boto3:
 
@@ -20,97 +21,23 @@ boto3:
 Nothing of the reference is copied: the loader only puts ``/root/reference`` on
 ``sys.path``.  ``available()`` tells callers whether the reference is present.
 """
-import os
-import sys
-import types
 
-REFERENCE_ROOT = os.environ.get("NUMS_REFERENCE_ROOT", "/root/reference")
+from nums_b200 import reference_compat
+
+REFERENCE_ROOT = reference_compat.reference_root() or "/root/reference"
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "nums", "core"))
-
-
-def _install_stubs():
-    import numpy as np
-
-    # -- removed numpy aliases -------------------------------------------------
-    for name, val in (("int", int), ("float", float), ("bool", np.bool_),
-                      ("object", object), ("complex", complex), ("str", str)):
-        if name not in np.__dict__:
-            setattr(np, name, val)
-    if "product" not in np.__dict__:
-        np.product = np.prod
-    for name, val in (("NINF", -np.inf), ("PINF", np.inf), ("PZERO", 0.0),
-                      ("NZERO", -0.0), ("Inf", np.inf), ("Infinity", np.inf),
-                      ("NaN", np.nan), ("NAN", np.nan), ("infty", np.inf)):
-        if name not in np.__dict__:
-            setattr(np, name, val)
-    st = np.lib.stride_tricks
-    if not hasattr(st, "broadcast_to"):
-        st.broadcast_to = np.broadcast_to
-
-    # -- numpy.compat ------------------------------------------------------------
-    try:
-        import numpy.compat as compat  # still a namespace on some builds
-    except Exception:  # pragma: no cover
-        compat = types.ModuleType("numpy.compat")
-        sys.modules["numpy.compat"] = compat
-    if not hasattr(compat, "asbytes"):
-        compat.asbytes = lambda s: s if isinstance(s, bytes) else str(s).encode("latin1")
-        compat.asstr = lambda s: s.decode("latin1") if isinstance(s, bytes) else str(s)
-        compat.asunicode = compat.asstr
-        compat.os_fspath = os.fspath
-        compat.contextlib_nullcontext = __import__("contextlib").nullcontext
-        compat.is_pathlib_path = lambda p: hasattr(p, "__fspath__")
-        sys.modules["numpy.compat"] = compat
-
-    # -- ray / boto3 -------------------------------------------------------------
-    if "ray" not in sys.modules:
-        ray = types.ModuleType("ray")
-        ray.__path__ = []
-
-        def _no_ray(*_a, **_k):
-            raise RuntimeError("ray is not installed; the oracle runs NUMS_SYSTEM=serial")
-
-        for fn in ("init", "shutdown", "put", "get", "remote", "nodes", "is_initialized"):
-            setattr(ray, fn, _no_ray)
-        raylet = types.ModuleType("ray._raylet")
-        raylet.ObjectRef = type("ObjectRef", (), {})
-        ray._raylet = raylet
-        actor = types.ModuleType("ray.actor")
-        actor.ActorHandle = type("ActorHandle", (), {})
-        ray.actor = actor
-        ray.ObjectRef = raylet.ObjectRef
-        sys.modules["ray"] = ray
-        sys.modules["ray._raylet"] = raylet
-        sys.modules["ray.actor"] = actor
-    if "boto3" not in sys.modules:
-        boto3 = types.ModuleType("boto3")
-        boto3.resource = lambda *a, **k: None
-        boto3.client = lambda *a, **k: None
-        sys.modules["boto3"] = boto3
-
-
-_loaded = None
+    return reference_compat.reference_root() is not None
 
 
 def load():
-    """Import the reference and return the ``nums`` package (serial system only)."""
-    global _loaded
-    if _loaded is not None:
-        return _loaded
+    """Import the reference and return the ``nums`` package (serial system only).  The numpy-2 /
+    no-ray shims live in ``nums_b200.reference_compat`` (they are also what lets the reference's host
+    layers run over ``cuda_compute``)."""
     if not available():
-        raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
-    os.environ.setdefault("NUMS_SYSTEM", "serial")
-    _install_stubs()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
-    import nums  # noqa: F401
-    from nums.core import settings
-    settings.system_name = "serial"
-    _loaded = nums
-    return nums
+        raise RuntimeError("reference not present (looked at $NUMS_REFERENCE_ROOT, /root/reference, baseline/_ref)")
+    return reference_compat.load_reference("serial")
 
 
 def serial_app(compute_module=None):
