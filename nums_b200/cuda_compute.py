@@ -111,7 +111,7 @@ def await_uploads(stream=None, upto=None):
     if _Transfers.last_event is None:
         return
     cur = torch.cuda.current_stream() if stream is None else stream
-    key = cur.cuda_stream
+    key = cur.cuda_stream       # torch streams come from a pool and are never destroyed: handles are not recycled
     seq, event = (_Transfers.seq, _Transfers.last_event) if upto is None else upto
     if _Transfers.awaited.get(key, 0) < seq:
         cur.wait_event(event)
@@ -141,6 +141,11 @@ def upload(value, dtype=None):
     Large page-locked sources (e.g. arrays backed by ``torch.empty(pin_memory=True)``) are copied
     asynchronously on the upload stream straight from where they are (see ``_Transfers``); pageable
     ones go through the driver's own staging on the current stream.
+
+    Ownership: for the asynchronous (page-locked, >= 1 MiB) path the copy reads the caller's buffer AFTER
+    this call returns -- the caller must not modify or free it until the block has been consumed (any
+    ``get`` / ``synchronize``), unlike the reference's ``put`` and the pageable path here, which snapshot
+    the array at the time of the call.
     """
     if isinstance(value, torch.Tensor):
         return value
@@ -173,6 +178,31 @@ def _upload_tensor(host):
         dev._nums_ready = (_Transfers.seq, event)
         return dev
     return host.to(_device())
+
+
+def upload_tag(t):
+    """``(sequence number, event)`` of the asynchronous upload that fills tensor ``t``, or None.
+
+    The tag is a Python attribute of the tensor object ``_upload_tensor`` returned, so views of it
+    (``transpose`` / ``reshape`` / ``split`` results, user slices) do not carry it; for those the base
+    tensor is consulted, and a view whose base cannot be identified is conservatively treated as
+    depending on the latest upload issued."""
+    if not isinstance(t, torch.Tensor):
+        return None
+    tag = getattr(t, "_nums_ready", None)
+    if tag is not None:
+        return tag
+    base = t._base
+    if base is not None:
+        tag = getattr(base, "_nums_ready", None)
+        if tag is not None:
+            return tag
+        if _Transfers.last_event is not None:
+            # a view of a view-less base without a tag was either computed on the device (no upload to wait
+            # for -- but then the kernel that produced it already ordered the stream) or its tagged Python
+            # object is gone: wait for everything uploaded so far
+            return (_Transfers.seq, _Transfers.last_event)
+    return None
 
 
 def _to_pinned(t):
@@ -261,8 +291,17 @@ def _scatter(dst, src, dst_index, src_index, outer, dst_len, src_len, inner):
                                         _stream()))
 
 
+def _carry_tag(view, src):
+    """Views are new Python objects: keep the upload tag of the tensor they alias."""
+    if view is not src:
+        tag = getattr(src, "_nums_ready", None)
+        if tag is not None:
+            view._nums_ready = tag
+    return view
+
+
 def _transpose_view(t):
-    return t.permute(*reversed(range(t.dim()))) if t.dim() > 1 else t
+    return _carry_tag(t.permute(*reversed(range(t.dim()))), t) if t.dim() > 1 else t
 
 
 def _reshape(t, shape):
@@ -270,7 +309,7 @@ def _reshape(t, shape):
     if tuple(t.shape) == shape:
         return t
     try:
-        return t.view(shape)
+        return _carry_tag(t.view(shape), t)
     except RuntimeError:
         return _materialize(t).view(shape)
 
@@ -512,7 +551,7 @@ class ComputeCls(_ComputeImp):
         else:
             cuts = [0] + [int(i) for i in indices_or_sections] + [n]
             bounds = [(min(cuts[i], n), min(max(cuts[i + 1], cuts[i]), n)) for i in range(len(cuts) - 1)]
-        return [arr.narrow(axis, lo, max(hi - lo, 0)) for lo, hi in bounds]
+        return [_carry_tag(arr.narrow(axis, lo, max(hi - lo, 0)), arr) for lo, hi in bounds]
 
     def astype(self, arr, dtype_str):
         arr = upload(arr)
@@ -973,10 +1012,26 @@ def _single_cta_factor(fn, arr, message):
     return out
 
 
+def _lr_operands(X, y, beta):
+    """The fused kernels read raw float64 pointers: X (n, d) with unit column stride, y (n,) and beta (d,)
+    dense.  Anything else is converted (y of another dtype, e.g. bool / int labels) or rejected."""
+    if X.dim() != 2 or X.dtype != torch.float64 or X.stride(1) != 1:
+        raise ValueError("lr_grad_hess: X must be a 2-D float64 block with unit column stride")
+    if y.dtype != torch.float64 or not y.is_contiguous():
+        y = _materialize(y, torch.float64)
+    if beta.dtype != torch.float64 or not beta.is_contiguous():
+        beta = _materialize(beta, torch.float64)
+    if y.numel() != X.shape[0] or beta.numel() != X.shape[1]:
+        raise ValueError("lr_grad_hess: shapes X %s, y %s, beta %s do not agree"
+                         % (tuple(X.shape), tuple(y.shape), tuple(beta.shape)))
+    return X, y, beta
+
+
 def lr_grad_hess(X, y, beta):
     """Fused g = X^T (mu - y), H = X^T diag(mu (1 - mu)) X for one row block (nums_lr_grad_hess).
 
     Returns a 1-D tensor of d + d*d doubles (g followed by row-major H)."""
+    X, y, beta = _lr_operands(X, y, beta)
     n, d = X.shape
     out = _empty((d + d * d,), np.float64)
     LIB.call_ws(LIB.dll.nums_lr_grad_hess, X.device,
@@ -987,6 +1042,8 @@ def lr_grad_hess(X, y, beta):
 def lr_grad_hess_blocks(x_blocks, y_blocks, beta):
     """g | H summed over a list of row blocks.  Dense blocks of a supported width go through
     nums_lr_grad_hess_blocks (16 blocks per launch); anything else block by block."""
+    checked = [_lr_operands(x, y, beta) for x, y in zip(x_blocks, y_blocks)]
+    x_blocks, y_blocks, beta = [c[0] for c in checked], [c[1] for c in checked], checked[0][2]
     d = x_blocks[0].shape[1]
     dense = ((d % 16 in (4, 12)) and d <= 48
              and all(x.is_contiguous() and x.dtype == torch.float64 and x.data_ptr() % 16 == 0 for x in x_blocks))

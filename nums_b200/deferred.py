@@ -164,7 +164,7 @@ class ContractionQueue(object):
         latest = None
         for term in d.terms:
             for src in term[5:]:
-                tag = getattr(src, "_nums_ready", None)
+                tag = cuda_compute.upload_tag(src)
                 if tag is not None and (latest is None or tag[0] > latest[0]):
                     latest = tag
         return latest

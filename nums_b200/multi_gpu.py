@@ -172,6 +172,12 @@ class SummaMatmul(object):
             return peer.publish({k: [a_blocks[(i, k)] for i in self.my_i] for k in ka},
                                 {k: [b_blocks[(k, j)] for j in self.my_j] for k in kb})
 
+        if isinstance(first, torch.Tensor) and first.is_cuda:
+            # blocks put() from page-locked memory may still be crossing PCIe on the upload stream; the stack
+            # copies below run on the current stream
+            from nums_b200 import cuda_compute
+            cuda_compute.await_uploads()
+
         def stack(blocks):
             first = blocks[0]
             if isinstance(first, np.ndarray):
@@ -339,10 +345,24 @@ class _PeerPanels(object):
         self.buf = symm.empty(total, dtype=self.dtype, device=self.device)
         self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
         self.streams = (torch.cuda.Stream(), torch.cuda.Stream())
-        self._recv = [None, None]     # per parity: ({k: A panel}, {k: B panel})
+        # Both receive sets are allocated now, on the current stream, before any product runs: allocating a set
+        # lazily when its parity is first used could hand the copy streams memory the caching allocator had just
+        # freed on the compute stream (e.g. the previous product's C blocks) while the GEMM still writes it.
+        self._recv = [self._new_recv_set(), self._new_recv_set()]     # per parity: ({k: A panel}, {k: B panel})
+        allocated = torch.cuda.Event()
+        allocated.record()
+        for stream in self.streams:
+            stream.wait_event(allocated)
         self._done = [None, None]     # per parity: event after the last GEMM that read the set
         self._product = 0
         self._remote = {}
+
+    def _new_recv_set(self):
+        s = self.s
+        return ({k: torch.empty(self.shape_a, dtype=self.dtype, device=self.device)
+                 for k in range(s.g) if k % s.pc != s.c},
+                {k: torch.empty(self.shape_b, dtype=self.dtype, device=self.device)
+                 for k in range(s.g) if k % s.pr != s.r})
 
     def _mine_a(self, k):
         off = (k // self.s.pc) * self.numel_a
@@ -387,12 +407,6 @@ class _PeerPanels(object):
         """Queue every panel transfer of one product; returns per k (A panel, B panel, works)."""
         s = self.s
         parity = self._product & 1
-        if self._recv[parity] is None:
-            self._recv[parity] = (
-                {k: torch.empty(self.shape_a, dtype=self.dtype, device=self.device)
-                 for k in range(s.g) if k % s.pc != s.c},
-                {k: torch.empty(self.shape_b, dtype=self.dtype, device=self.device)
-                 for k in range(s.g) if k % s.pr != s.r})
         recv_a, recv_b = self._recv[parity]
         for stream in self.streams:
             stream.wait_event(published.ready)
