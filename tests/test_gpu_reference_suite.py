@@ -28,8 +28,11 @@ SERIAL_PASSED = sorted(k for k, v in SERIAL.items() if v == "passed")
 
 
 def _cuda_id(serial_id):
-    assert serial_id.endswith("serial]")
-    return serial_id[:-len("serial]")] + "cuda]"
+    """Tests that take app_inst / nps_app_inst carry the mode in their id; the others (pure host index
+    algebra in test_selection.py / test_broadcasting.py, test_explicit_init) have the same id in both runs."""
+    if serial_id.endswith("serial]"):
+        return serial_id[:-len("serial]")] + "cuda]"
+    return serial_id
 
 
 @pytest.fixture(scope="session")
