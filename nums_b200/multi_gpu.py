@@ -62,6 +62,7 @@ class Comm(object):
         self.rank = dist.get_rank() if self.enabled else 0
         self.world = dist.get_world_size() if self.enabled else 1
         self._groups = {}
+        self._side = None
 
     def group(self, ranks):
         """Sub-communicator for `ranks` (every rank must call this in the same order)."""
@@ -107,6 +108,57 @@ class Comm(object):
     def barrier(self):
         if self.enabled and self.world > 1:
             dist.barrier()
+
+    # -- used by nums_b200.spmd -----------------------------------------------------------------------
+    def setup_side_channel(self):
+        """A gloo group for small pickled messages (result descriptions, seeds): a host-side exchange that
+        does not touch the GPU streams.  Collective: every rank calls it once."""
+        if self.enabled and self.world > 1 and self._side is None:
+            self._side = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+
+    def broadcast_object(self, obj, src):
+        if not self.enabled or self.world == 1:
+            return obj
+        if self._side is None:
+            self.setup_side_channel()
+        box = [obj]
+        dist.broadcast_object_list(box, src=src, group=self._side)
+        return box[0]
+
+    def exchange(self, sends, recvs, order):
+        """One batched point-to-point exchange.  ``order`` lists (src, dst) of every transfer of the plan in
+        the same order on all ranks; ``sends`` = [(buffer, dst)] and ``recvs`` = [(buffer, src)] are this
+        rank's part of it, in plan order."""
+        if not self.enabled or self.world == 1:
+            return
+        ops, si, ri = [], 0, 0
+        for src, dst in order:
+            if self.rank == src:
+                t, _ = self._as_tensor(sends[si][0])
+                ops.append(dist.P2POp(dist.isend, t, dst))
+                si += 1
+            elif self.rank == dst:
+                t, _ = self._as_tensor(recvs[ri][0])
+                ops.append(dist.P2POp(dist.irecv, t, src))
+                ri += 1
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+
+def init_distributed():
+    """torchrun environment -> (rank, world): one process per GPU, NCCL over NVLink (RANK / LOCAL_RANK /
+    WORLD_SIZE / MASTER_* from the environment).  No-op when the process group exists or world is 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and not (dist.is_available() and dist.is_initialized()):
+        if torch.cuda.is_available():
+            local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=nccl_options())
+        else:
+            dist.init_process_group("gloo")
+    return rank, world
 
 
 def _empty_like_block(system, shape, like):

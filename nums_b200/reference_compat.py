@@ -189,13 +189,46 @@ def cuda_system_class():
     return _system_cls
 
 
+_spmd_cls = None
+
+
+def spmd_system_class():
+    """``SpmdSystem`` (nums_b200.spmd) in the same place of the reference's class hierarchy."""
+    global _spmd_cls
+    if _spmd_cls is None:
+        load_reference()
+        from nums.core.systems.systems import SerialSystem
+        from nums_b200.spmd import SpmdSystem
+
+        class ReferenceSpmdSystem(SpmdSystem, SerialSystem):
+            pass
+
+        _spmd_cls = ReferenceSpmdSystem
+    return _spmd_cls
+
+
+def cuda_system(**system_kwargs):
+    """The system object for this process: ``CudaSystem`` on one GPU; under ``torchrun`` (WORLD_SIZE > 1, one
+    process per GPU) an ``SpmdSystem`` that partitions the block grid over the ranks."""
+    from nums_b200 import multi_gpu
+    rank, world = multi_gpu.init_distributed()
+    if world > 1:
+        from nums_b200.cuda_system import CudaSystem
+        local = CudaSystem(rank=rank, world_size=world, **system_kwargs)
+        local.init()
+        system = spmd_system_class()(local)
+    else:
+        system = cuda_system_class()(**system_kwargs)
+    system.init()
+    return system
+
+
 def cuda_app(**system_kwargs):
-    """The reference's ``ArrayApplication`` on this process' GPU -- ``get_app("cuda")``."""
+    """The reference's ``ArrayApplication`` on this process' GPU(s) -- ``get_app("cuda")``."""
     load_reference()
     from nums.core.array.application import ArrayApplication
     from nums.core.systems.filesystem import FileSystem
-    system = cuda_system_class()(**system_kwargs)
-    system.init()
+    system = cuda_system(**system_kwargs)
     return ArrayApplication(system=system, filesystem=FileSystem(system))
 
 

@@ -1,0 +1,814 @@
+"""``SpmdSystem`` -- the block grid partitioned over the GPUs of one box, behind the unchanged kernel interface.
+
+The reference scales by handing every per-block kernel call to Ray together with
+``syskwargs={"grid_entry", "grid_shape"}`` and letting the scheduler pick a node
+(/root/reference/nums/core/systems/schedulers.py:170-246); operands travel through the object store.
+Here one process drives one GPU (``torchrun``) and EVERY rank runs the same, unmodified host program
+(``BlockArray`` / ``ArrayApplication`` / ``glms.newton``): each kernel call reaches this system on all ranks
+with identical arguments, the ranks agree -- without talking -- on who executes it, and only that rank
+launches the kernel.  What the host layers hold as ``oid`` is a ``Handle``: the same object on every rank
+(id, home rank, shape, dtype), with the device tensor attached only where the block lives.
+
+* **Placement** (SURVEY.md 8e): a call runs where most of its operand bytes already are ("compute where the
+  operands live", the fork's rule, gpu_systems.py:156-161); ties and calls without device-resident operands
+  go to ``owner(grid_entry, grid_shape)`` -- row-major flattened entry ``mod world`` for grids with one long
+  axis (gpu_systems.py:163-164), ``(i mod pr, j mod pc)`` on the ``pr x pc`` device grid for true 2-D grids
+  (BlockCyclicScheduler.get_cluster_entry, schedulers.py:170-191).  Blocks made by ``put`` and results of
+  single-block arrays (scalars, beta, the d x d Hessian, R) are *replicated*: every rank holds them and
+  computes on them redundantly, which costs nothing and removes all small-message traffic.
+* **Operand movement**: a remote operand is sent point to point (NCCL over NVLink) to the executing rank and
+  cached there (blocks are immutable, numpy_compute.py:136-138).
+* **Reductions across ranks** (the reference gathers to one node: ``sum_reduce`` in ``_matvec``,
+  blockarray.py:574-578; the ``add`` chains of ``_tensordot`` :468-471 and of ``reduce_axis`` :402-407; the
+  stacked ``qr(*R_oids)``, application.py:807-814): ``sum_reduce`` over blocks living on several ranks is a
+  local partial sum + ONE all-reduce; ``tensordot`` / ``add`` chains are recorded lazily (``_Lazy``) and
+  materialised together -- operands that must move are exchanged in one batched transfer, every rank
+  contracts its own terms in one grouped DMMA launch (CudaSystem's deferred contractions), and results whose
+  terms live on several ranks are all-reduced; the stacked-R ``qr`` is a local QR + binary tree over the
+  ranks + broadcast.  Results of cross-rank reductions are replicated.
+* ``get`` broadcasts from the home rank, so every rank's host program sees the same values (it may branch
+  on them: ``if max(abs(g)) <= tol``, glms.py:370).
+
+Shapes / dtypes of results must be known on ranks that do not execute a call (receive buffers, later
+placement decisions): they are inferred for the kernels on the hot path (``infer_result``) and, for the rest
+(dynamic sizes such as ``where``, registered I/O functions), broadcast as a small pickled description from
+the executing rank over a gloo side channel.  ``NUMS_SPMD_CHECK=1`` asserts inference == actual.
+
+The class is backend-agnostic: ``local`` is a ``CudaSystem`` in production and the oracle system (NumPy
+blocks, gloo) in the CPU tests (tests/test_spmd_cpu.py), which is how the host logic is covered without a GPU.
+"""
+import os
+import weakref
+
+import numpy as np
+
+REPLICATED = -1
+_NOT_HANDLED = object()
+_BOP_PARAMS = ("op", "a1", "a2", "a1_shape", "a2_shape", "a1_T", "a2_T", "axes")
+LAZY_MIN_EXTENT = 64            # same eligibility as CudaSystem's deferred contractions (deferred.py)
+PROMOTE_BYTES = 1 << 20         # fetched blocks up to this size stay on every rank
+COALESCE_BYTES = 1 << 20        # all-reduces of partials up to this size share one buffer
+
+
+class Handle(object):
+    """One block of the distributed array store; identical metadata on every rank."""
+    __slots__ = ("hid", "home", "value", "shape", "dtype", "copies", "lazy", "__weakref__")
+
+    def __init__(self, hid, home, value, shape, dtype):
+        self.hid = hid
+        self.home = home                  # owning rank, or REPLICATED
+        self.value = value                # local block where available, else None
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.copies = ()                  # ranks (besides home) that hold a cached copy
+        self.lazy = None                  # _Lazy while the value is still an unevaluated sum
+
+    def available_on(self, rank):
+        return self.home == REPLICATED or self.home == rank or rank in self.copies
+
+    @property
+    def nbytes(self):
+        return int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+
+    def __repr__(self):
+        return "Handle(#%d home=%s %s %s%s)" % (self.hid, "*" if self.home == REPLICATED else self.home, self.shape,
+                                                self.dtype, " lazy" if self.lazy is not None else "")
+
+
+class _Lazy(object):
+    """value = sum of ``items`` in order; an item is ("dot", a1, a2, a1_shape, a2_shape, a1_T, a2_T, rank) --
+    np.tensordot(a1, a2, 1) evaluated on ``rank`` -- or ("blk", handle, rank)."""
+    __slots__ = ("items", "hint")
+
+    def __init__(self, items, hint):
+        self.items = items
+        self.hint = hint
+
+    def ranks(self):
+        return sorted({it[-1] for it in self.items})
+
+
+# -----------------------------------------------------------------------------------------------------
+# local back ends: what SpmdSystem needs besides the kernel interface
+# -----------------------------------------------------------------------------------------------------
+class _TorchBackend(object):
+    def __init__(self, system):
+        self.system = system
+
+    def is_block(self, v):
+        import torch
+        from nums_b200.deferred import DeferredContraction
+        return isinstance(v, (torch.Tensor, DeferredContraction))
+
+    def concrete(self, v):
+        """A dense tensor holding the block (launches whatever the local system still defers)."""
+        from nums_b200 import cuda_compute
+        v = self.system.contractions.resolve(v)
+        return v if v.is_contiguous() else cuda_compute._materialize(v)
+
+    def settle(self, v):
+        """The tensor behind a (by now launched) deferred contraction; other values unchanged."""
+        return self.system.contractions.resolve(v)
+
+    def meta(self, v):
+        from nums_b200 import _lib
+        return tuple(int(s) for s in v.shape), _lib.numpy_dtype(v.dtype)
+
+    def empty(self, shape, dtype):
+        from nums_b200 import cuda_compute
+        return cuda_compute._empty(shape, dtype)
+
+    def zeros(self, shape, dtype):
+        from nums_b200 import cuda_compute
+        from nums_b200._lib import LIB, describe
+        out = cuda_compute._empty(shape, dtype)
+        if out.numel():
+            LIB.check(LIB.dll.nums_fill(describe(out), 0.0, cuda_compute._stream()))
+        return out
+
+    def clone(self, v):
+        from nums_b200 import cuda_compute
+        return cuda_compute._materialize(self.system.contractions.resolve(v))
+
+    def copy_into(self, dst, src):
+        from nums_b200 import cuda_compute
+        cuda_compute._copy_into(dst, src)
+
+    def flat_view(self, buf, offset, shape):
+        n = int(np.prod(shape, dtype=np.int64))
+        return buf[offset:offset + n].view(tuple(shape))
+
+    def flush(self):
+        self.system.flush()
+
+    def synchronize(self):
+        self.system.synchronize()
+
+
+class _NumpyBackend(object):
+    def __init__(self, system):
+        self.system = system
+
+    def is_block(self, v):
+        return isinstance(v, (np.ndarray, np.generic))
+
+    def concrete(self, v):
+        return np.ascontiguousarray(v)
+
+    def settle(self, v):
+        return v
+
+    def meta(self, v):
+        v = np.asarray(v)
+        return tuple(v.shape), v.dtype
+
+    def empty(self, shape, dtype):
+        return np.empty(shape, dtype=dtype)
+
+    def zeros(self, shape, dtype):
+        return np.zeros(shape, dtype=dtype)
+
+    def clone(self, v):
+        return np.array(v, copy=True)
+
+    def copy_into(self, dst, src):
+        dst[...] = src
+
+    def flat_view(self, buf, offset, shape):
+        n = int(np.prod(shape, dtype=np.int64))
+        return buf[offset:offset + n].reshape(tuple(shape))
+
+    def flush(self):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+# -----------------------------------------------------------------------------------------------------
+# result shapes / dtypes without executing (hot-path kernels only; None = ask the executing rank)
+# -----------------------------------------------------------------------------------------------------
+def _broadcast(s1, s2):
+    return tuple(int(x) for x in np.broadcast_shapes(tuple(s1), tuple(s2)))
+
+
+def _float_like(dt):
+    return np.dtype(np.float32) if np.dtype(dt) == np.float32 else np.dtype(np.float64)
+
+
+def infer_result(name, args, kwargs, meta_of):
+    """Description of what kernel ``name`` returns -- ("b", shape, dtype str) per block, ("t", [...]) for
+    tuples -- from the arguments alone, or None when it cannot be told cheaply.  ``meta_of(x)`` gives
+    (shape, dtype) of a block argument."""
+    from nums_b200 import cuda_compute as cc
+    from nums_b200.grid import ArrayGrid
+
+    def blk(shape, dtype):
+        return ("b", tuple(int(s) for s in shape), np.dtype(dtype).str)
+
+    try:
+        if name == "bop":
+            b = dict(zip(_BOP_PARAMS, args))
+            b.update(kwargs)
+            op = b["op"]
+            (_s1, d1), (_s2, d2) = meta_of(b["a1"]), meta_of(b["a2"])
+            s1, s2 = tuple(b["a1_shape"]), tuple(b["a2_shape"])
+            if op == "tensordot":
+                axes = int(b["axes"])
+                dt = np.result_type(d1, d2)
+                if dt == np.bool_:
+                    return None
+                return blk(s1[:len(s1) - axes] + s2[axes:], dt)
+            ufunc = cc._SHORT_OP_NAMES.get(op, op)
+            return blk(_broadcast(s1, s2), cc.bop_types(ufunc, np.dtype(d1), np.dtype(d2))[1])
+        if name == "map_uop":
+            op_name, arr = args[0], args[1]
+            if (len(args) > 2 and args[2]) or (len(args) > 3 and args[3]):
+                return None
+            shape, dt = meta_of(arr)
+            return blk(shape, cc.uop_types(op_name, np.dtype(dt))[1])
+        if name == "reduce_axis":
+            b = dict(zip(("op_name", "arr", "axis", "keepdims", "transposed"), args))
+            b.update(kwargs)
+            shape, dt = meta_of(b["arr"])
+            if b["transposed"]:
+                shape = tuple(reversed(shape))
+            nd, axis = len(shape), b["axis"]
+            if axis is None:
+                out = (1,) * nd if b["keepdims"] else ()
+            else:
+                axis = int(axis) % nd
+                out = shape[:axis] + ((1,) if b["keepdims"] else ()) + shape[axis + 1:]
+            return blk(out, cc.reduce_type(b["op_name"], np.dtype(dt)))
+        if name == "sum_reduce":
+            metas = [meta_of(a) for a in args]
+            return blk(metas[0][0], np.result_type(*[m[1] for m in metas]))
+        if name in ("new_block", "empty"):
+            entry, grid_meta = args[-2], args[-1]
+            grid = ArrayGrid.from_meta(grid_meta)
+            return blk(grid.get_block_shape(entry), np.dtype(grid.dtype))
+        if name == "transpose":
+            shape, dt = meta_of(args[0])
+            return blk(tuple(reversed(shape)), dt)
+        if name == "reshape":
+            shape = args[1] if len(args) > 1 else kwargs["shape"]
+            shape = tuple(shape) if isinstance(shape, (tuple, list)) else (shape,)
+            if any(int(s) < 0 for s in shape):
+                return None
+            return blk(shape, meta_of(args[0])[1])
+        if name == "astype":
+            return blk(meta_of(args[0])[0], cc._np_dtype(args[1] if len(args) > 1 else kwargs["dtype_str"]))
+        if name in ("inv", "cholesky"):
+            shape, dt = meta_of(args[0])
+            return blk(shape, _float_like(dt))
+        if name == "xlogy":
+            (s1, _d1), (s2, _d2) = meta_of(args[0]), meta_of(args[1])
+            return blk(_broadcast(s1, s2), np.float64)
+        if name == "qr":
+            metas = [meta_of(a) for a in args]
+            mode, axis = kwargs.get("mode", "reduced"), kwargs.get("axis")
+            if any(len(m[0]) != 2 for m in metas):
+                return None
+            if len(metas) > 1:
+                axis = int(axis)
+                rows = sum(m[0][0] for m in metas) if axis == 0 else metas[0][0][0]
+                cols = metas[0][0][1] if axis == 0 else sum(m[0][1] for m in metas)
+            else:
+                rows, cols = metas[0][0]
+            dt = _float_like(np.result_type(*[m[1] for m in metas]))
+            k = min(rows, cols)
+            if mode == "r":
+                return blk((k, cols), dt)
+            if mode == "reduced":
+                return ("t", [blk((rows, k), dt), blk((k, cols), dt)])
+            return None
+        if name == "create_block":
+            return blk(kwargs["dst_shape"], meta_of(args[0])[1])
+        if name in ("update_block_by_index", "update_block_along_axis"):
+            shape, dt = meta_of(args[0])
+            return blk(shape, dt)
+    except Exception:  # noqa: BLE001 -- anything unusual: let the executing rank describe the result
+        return None
+    return None
+
+
+class SpmdSystem(object):
+    """See the module docstring.  ``local`` executes kernels on this rank; ``comm`` is a ``multi_gpu.Comm``."""
+
+    def __init__(self, local, comm=None, placement="auto", check=None):
+        from nums_b200 import multi_gpu
+        self.methods = {}         # first: the reference's System.__getattribute__ (systems.py:62-66) reads it on every access
+        self.remote_functions = {}
+        self.local = local
+        self.comm = comm if comm is not None else multi_gpu.Comm()
+        self.rank, self.world_size = self.comm.rank, self.comm.world
+        self.placement = placement
+        self.device_grid = multi_gpu.device_grid(self.world_size)
+        self.check = bool(int(os.environ.get("NUMS_SPMD_CHECK", "0"))) if check is None else bool(check)
+        self.backend = _TorchBackend(local) if hasattr(local, "contractions") else _NumpyBackend(local)
+        self.compute_module = getattr(local, "compute_module", None)
+        self.compute_imp = getattr(local, "compute_imp", None)
+        self.rng_cls = getattr(local, "rng_cls", None)
+        self._registered = set()
+        self._next = 0
+        self._lazies = []
+        self._copied = weakref.WeakSet()      # handles with cached copies away from home
+        self.stats = {"moves": 0, "moved_bytes": 0, "all_reduces": 0, "broadcasts": 0, "meta_broadcasts": 0,
+                      "executed": 0, "skipped": 0, "replicated": 0, "flushes": 0}
+
+    # -- lifecycle ------------------------------------------------------------------------------------
+    def init(self):
+        if hasattr(self.local, "init") and not getattr(self.local, "remote_functions", None):
+            self.local.init()
+        names = getattr(self.local, "remote_functions", None)
+        if names is None:      # the oracle system of the CPU tests: kernel names from its implementation
+            names = [n for n in dir(self.local.imp) if not n.startswith("_") and callable(getattr(self.local.imp, n))]
+        for name in names:
+            self.remote_functions[name] = name
+            self.methods[name] = self._make_callable(name)
+        self.comm.setup_side_channel()
+
+    def shutdown(self):
+        self.flush()
+
+    def _make_callable(self, name):
+        def kernel(*args, **kwargs):
+            return self.call(name, *args, **kwargs)
+        kernel.__name__ = name
+        return kernel
+
+    def __getattr__(self, name):
+        methods = self.__dict__.get("methods", {})
+        if name in methods:
+            return methods[name]
+        raise AttributeError(name)
+
+    def remote(self, function, remote_params):
+        return function
+
+    def register(self, name, func, remote_params=None):
+        """Registered (I/O) functions run on exactly ONE rank -- they have side effects."""
+        if name in self.remote_functions:
+            return
+        self.local.register(name, func, remote_params)
+        self.remote_functions[name] = name
+        self.methods[name] = self._make_callable(name)
+        self._registered.add(name)
+
+    def nodes(self):
+        return [{"Resources": {"node:%d" % r: 1.0}} for r in range(self.world_size)]
+
+    def get_rng(self, seed):
+        if seed is None:        # every rank must hand out the same (seed, jump_index) pairs
+            import random
+            seed = self.comm.broadcast_object(random.getrandbits(128) if self.rank == 0 else None, 0)
+        return self.rng_cls(seed)
+
+    def get_options(self, cluster_entry, cluster_shape):
+        return {"resources": {"node:%d" % self.owner(tuple(cluster_entry), tuple(cluster_shape)): 1.0 / 10 ** 4}}
+
+    def get_block_addresses(self, grid):
+        return {entry: "node:%d" % self.owner(entry, grid.grid_shape) for entry in grid.get_entry_iterator()}
+
+    def call_with_options(self, name, args, kwargs, options):
+        rank = None
+        for key in (options or {}).get("resources", {}):
+            if isinstance(key, str) and key.startswith("node:"):
+                rank = int(key.split(":")[1])
+        return self.call(name, *args, _rank=rank, **kwargs)
+
+    # -- placement ------------------------------------------------------------------------------------
+    def owner(self, grid_entry, grid_shape):
+        """Rank that executes calls scheduled on ``grid_entry`` of a grid of ``grid_shape`` when the operands
+        do not decide it."""
+        if self.world_size == 1 or len(grid_entry) == 0:
+            return 0
+        long_axes = [i for i, g in enumerate(grid_shape) if g > 1]
+        if self.placement == "flat" or len(long_axes) <= 1:
+            return int(np.ravel_multi_index(tuple(grid_entry), tuple(grid_shape))) % self.world_size
+        pr, pc = self.device_grid
+        a0, a1 = long_axes[0], long_axes[1]
+        return (grid_entry[a0] % pr) * pc + (grid_entry[a1] % pc)
+
+    def _hint(self, sysk, rank=None):
+        if rank is not None:
+            return rank % self.world_size
+        if not sysk or "grid_entry" not in sysk:
+            return None
+        return self.owner(tuple(sysk["grid_entry"]), tuple(sysk["grid_shape"]))
+
+    def _exec_rank(self, handles, sysk, single, rank=None):
+        owned = [h for h in handles if h.home != REPLICATED]
+        hint = self._hint(sysk, rank)
+        if owned:
+            score = {}
+            for h in owned:
+                for r in (h.home,) + tuple(h.copies):
+                    score[r] = score.get(r, 0) + h.nbytes
+            best = max(score.values())
+            ranks = sorted(r for r, s in score.items() if s == best)
+            return hint if hint in ranks else ranks[0]
+        if single:
+            return hint if hint is not None else 0
+        if hint is None or sysk is None or int(np.prod(sysk.get("grid_shape", ()), dtype=np.int64)) <= 1:
+            return REPLICATED
+        return hint
+
+    # -- handles --------------------------------------------------------------------------------------
+    def _new_handle(self, home, value, shape, dtype):
+        self._next += 1
+        return Handle(self._next, home, value, shape, dtype)
+
+    def _meta_of(self, x):
+        if isinstance(x, Handle):
+            return x.shape, x.dtype
+        return self.backend.meta(x)
+
+    def _describe(self, r):
+        if self.backend.is_block(r):
+            shape, dt = self.backend.meta(r)
+            return ("b", tuple(shape), np.dtype(dt).str)
+        if isinstance(r, tuple):
+            return ("t", [self._describe(x) for x in r])
+        if isinstance(r, list):
+            return ("l", [self._describe(x) for x in r])
+        return ("v", r)
+
+    def _wrap(self, result, desc, home):
+        """Handles for a kernel result: ``result`` is the actual value on ranks that executed, else None."""
+        kind = desc[0]
+        if kind == "b":
+            return self._new_handle(home, result, desc[1], np.dtype(desc[2]))
+        if kind in ("t", "l"):
+            items = [self._wrap(None if result is None else result[i], d, home) for i, d in enumerate(desc[1])]
+            return tuple(items) if kind == "t" else items
+        return desc[1]
+
+    def _unwrap(self, x):
+        if isinstance(x, Handle):
+            return x.value
+        if isinstance(x, (list, tuple)) and any(isinstance(v, Handle) for v in x):
+            return type(x)(self._unwrap(v) for v in x)
+        return x
+
+    @staticmethod
+    def _handles_in(args, kwargs):
+        out = []
+        for v in list(args) + list(kwargs.values()):
+            if isinstance(v, Handle):
+                out.append(v)
+            elif isinstance(v, (list, tuple)):
+                out.extend(h for h in v if isinstance(h, Handle))
+        return out
+
+    # -- object store ---------------------------------------------------------------------------------
+    def put(self, value):
+        block = self.local.put(value)
+        shape, dt = self.backend.meta(block)
+        return self._new_handle(REPLICATED, block, shape, dt)
+
+    def put_at(self, value, grid_entry, grid_shape):
+        """``put`` for callers that know where the block belongs (the reference's ``put`` carries no placement
+        information, systems.py:94-95, so plain ``put`` replicates): only ``owner(grid_entry, grid_shape)``
+        uploads ``value``; the other ranks may pass ``None`` or an array of the same shape and dtype (ignored)
+        plus, when they pass ``None``, must call with ``like=(shape, dtype)`` semantics via ``value`` being a
+        ``(shape, dtype)`` tuple."""
+        home = self.owner(tuple(grid_entry), tuple(grid_shape))
+        if isinstance(value, tuple) and len(value) == 2 and not hasattr(value, "shape"):
+            shape, dt = value
+            assert self.rank != home, "the owner must pass the data"
+            return self._new_handle(home, None, shape, np.dtype(dt))
+        arr = value
+        shape, dt = tuple(arr.shape), (np.dtype(arr.dtype) if isinstance(arr, np.ndarray) else self.backend.meta(arr)[1])
+        block = self.local.put(arr) if self.rank == home else None
+        return self._new_handle(home, block, shape, dt)
+
+    def evict_copies(self):
+        """Forget every cached copy of a remote block (the blocks themselves stay at home).  Operand copies
+        are kept by default because blocks are immutable; a benchmark that wants every product to pay for
+        its exchange calls this between steps."""
+        for h in list(self._copied):
+            if h.home != REPLICATED and h.home != self.rank:
+                h.value = None
+            h.copies = ()
+        self._copied = weakref.WeakSet()
+
+    def get(self, oids):
+        self.flush()
+        seen = {}
+
+        def walk(o):
+            if isinstance(o, Handle):
+                if o.hid not in seen:
+                    seen[o.hid] = self._fetch(o)
+                return seen[o.hid]
+            if isinstance(o, list):
+                return [walk(v) for v in o]
+            if isinstance(o, tuple):
+                return tuple(walk(v) for v in o)
+            return o
+        local_values = walk(oids)
+        return self.local.get(local_values)
+
+    def _fetch(self, h):
+        """The block of ``h`` on THIS rank (broadcast from its home when it is not replicated)."""
+        if h.home == REPLICATED:
+            return h.value
+        src = h.home
+        if self.rank == src:
+            buf = self.backend.concrete(h.value)
+        else:
+            buf = self.backend.empty(h.shape, h.dtype)
+        self.comm.broadcast(buf, src)
+        self.stats["broadcasts"] += 1
+        if h.nbytes <= PROMOTE_BYTES:
+            if self.rank != src:
+                h.value = buf
+            h.home = REPLICATED
+        return buf
+
+    def flush_and_sync(self):
+        self.flush()
+        self.backend.synchronize()
+
+    synchronize = flush_and_sync
+
+    # -- transfers ------------------------------------------------------------------------------------
+    def _move_many(self, moves):
+        """[(handle, dst)]: make each block available on ``dst`` (cached there).  One batched exchange."""
+        moves = [(h, dst) for h, dst in moves if not h.available_on(dst)]
+        if not moves:
+            return
+        sends, recvs = [], []
+        for h, dst in moves:
+            src = h.home
+            if self.rank == src:
+                sends.append((self.backend.concrete(h.value), dst))
+            elif self.rank == dst:
+                buf = self.backend.empty(h.shape, h.dtype)
+                recvs.append((buf, src))
+                h.value = buf
+            h.copies = tuple(h.copies) + (dst,)
+            self._copied.add(h)
+            self.stats["moves"] += 1
+            self.stats["moved_bytes"] += h.nbytes
+        self.comm.exchange(sends, recvs, order=[(h.home, dst) for h, dst in moves])
+
+    # -- dispatch -------------------------------------------------------------------------------------
+    def call(self, name, *args, **kwargs):
+        kwargs = dict(kwargs)
+        sysk = kwargs.pop("syskwargs", None)
+        rank = kwargs.pop("_rank", None)
+        if name == "touch":
+            self.flush()
+            return True
+        special = getattr(self, "_k_" + name, None)
+        if special is not None:
+            out = special(args, kwargs, sysk)
+            if out is not _NOT_HANDLED:
+                return out
+        return self._generic(name, args, kwargs, sysk, rank)
+
+    def _generic(self, name, args, kwargs, sysk, rank=None):
+        handles = self._handles_in(args, kwargs)
+        if any(h.lazy is not None for h in handles):
+            self.flush()
+        single = name in self._registered
+        e = self._exec_rank(handles, sysk, single, rank)
+        if e == REPLICATED:
+            self.stats["replicated"] += 1
+            result = self.local.call(name, *[self._unwrap(a) for a in args], **{k: self._unwrap(v) for k, v in kwargs.items()})
+            return self._wrap(result, self._describe(result), REPLICATED)
+        desc = None if single else infer_result(name, args, kwargs, self._meta_of)
+        self._move_many([(h, e) for h in handles])
+        if self.rank == e:
+            self.stats["executed"] += 1
+            error = None
+            try:
+                result = self.local.call(name, *[self._unwrap(a) for a in args],
+                                         **{k: self._unwrap(v) for k, v in kwargs.items()})
+            except Exception as exc:  # noqa: BLE001
+                if desc is not None:
+                    raise
+                error, result = exc, None
+            if desc is None:
+                self.stats["meta_broadcasts"] += 1
+                payload = ("error", repr(error)) if error is not None else ("ok", self._describe(result))
+                self.comm.broadcast_object(payload, e)
+                if error is not None:
+                    raise error
+                desc = payload[1]
+            elif self.check:
+                actual = self._describe(result)
+                if actual != desc:
+                    raise AssertionError("SPMD result inference mismatch for %s: inferred %r, actual %r" % (name, desc, actual))
+            return self._wrap(result, desc, e)
+        self.stats["skipped"] += 1
+        if desc is None:
+            self.stats["meta_broadcasts"] += 1
+            status, desc = self.comm.broadcast_object(None, e)
+            if status == "error":
+                raise RuntimeError("kernel %s failed on rank %d: %s" % (name, e, desc))
+        return self._wrap(None, desc, e)
+
+    # -- lazily summed contractions ---------------------------------------------------------------------
+    def _lazy_handle(self, items, hint, shape, dtype):
+        lazy = _Lazy(items, hint)
+        ranks = lazy.ranks()
+        h = self._new_handle(ranks[0] if len(ranks) == 1 else REPLICATED, None, shape, dtype)
+        h.lazy = lazy
+        self._lazies.append(weakref.ref(h))
+        return h
+
+    def _term_rank(self, a1, a2, hint):
+        if a1.home == REPLICATED and a2.home == REPLICATED:
+            return hint
+        for cand in ([hint] if hint is not None else []) + [a1.home, a2.home]:
+            if cand != REPLICATED and a1.available_on(cand) and a2.available_on(cand):
+                return cand
+        return hint if hint is not None else (a1.home if a1.home != REPLICATED else a2.home)
+
+    def _k_bop(self, args, kwargs, sysk):
+        bound = dict(zip(_BOP_PARAMS, args))
+        bound.update(kwargs)
+        if len(bound) != len(_BOP_PARAMS):
+            return _NOT_HANDLED
+        op, a1, a2 = bound["op"], bound["a1"], bound["a2"]
+        if not (isinstance(a1, Handle) and isinstance(a2, Handle)):
+            return _NOT_HANDLED
+        f64 = np.dtype(np.float64)
+        if op == "tensordot":
+            s1, s2 = tuple(bound["a1_shape"]), tuple(bound["a2_shape"])
+            if (a1.lazy is None and a2.lazy is None and bound["axes"] == 1 and len(s1) == 2 and len(s2) == 2
+                    and a1.dtype == f64 and a2.dtype == f64 and s1[1] == s2[0]
+                    and s1[0] >= LAZY_MIN_EXTENT and s2[1] >= LAZY_MIN_EXTENT and s1[1] >= 1):
+                hint = self._hint(sysk)
+                hint = 0 if hint is None else hint
+                item = ("dot", a1, a2, s1, s2, bool(bound["a1_T"]), bool(bound["a2_T"]), self._term_rank(a1, a2, hint))
+                return self._lazy_handle([item], hint, (s1[0], s2[1]), f64)
+            return _NOT_HANDLED
+        if op == "add" and not bound["a1_T"] and not bound["a2_T"] and a1.dtype == f64 and a2.dtype == f64 \
+                and tuple(bound["a1_shape"]) == tuple(bound["a2_shape"]) == a1.shape == a2.shape:
+            hint = self._hint(sysk)
+            if a1.lazy is not None or a2.lazy is not None:
+                lazy_hint = (a1.lazy or a2.lazy).hint
+                items = []
+                for h in (a1, a2):
+                    if h.lazy is not None:
+                        items.extend(h.lazy.items)
+                    else:
+                        items.append(("blk", h, h.home if h.home != REPLICATED else lazy_hint))
+                return self._lazy_handle(items, lazy_hint, a1.shape, f64)
+            if (a1.home != REPLICATED and a2.home != REPLICATED and a1.home != a2.home
+                    and not a1.available_on(a2.home) and not a2.available_on(a1.home)):
+                # partial results living on different ranks (the add chains of _tensordot / reduce_axis):
+                # summed where they are and all-reduced, instead of being shipped to one rank one by one
+                items = [("blk", a1, a1.home), ("blk", a2, a2.home)]
+                return self._lazy_handle(items, 0 if hint is None else hint, a1.shape, f64)
+        return _NOT_HANDLED
+
+    def flush(self):
+        """Materialise every lazy sum that is still referenced (identical plan on every rank)."""
+        alive = []
+        for ref in self._lazies:
+            h = ref()
+            if h is not None and h.lazy is not None:
+                alive.append(h)
+        self._lazies = []
+        if not alive:
+            self.backend.flush()
+            return
+        self.stats["flushes"] += 1
+        # A. operands that must travel: one batched exchange
+        moves, seen = [], set()
+        for h in alive:
+            for it in h.lazy.items:
+                if it[0] != "dot":
+                    continue
+                for operand in (it[1], it[2]):
+                    key = (operand.hid, it[-1])
+                    if key not in seen and not operand.available_on(it[-1]):
+                        seen.add(key)
+                        moves.append((operand, it[-1]))
+        self._move_many(moves)
+        # B. every rank evaluates its own terms (CudaSystem defers them into one grouped launch)
+        partial, borrowed = {}, {}
+        for h in alive:
+            acc, count = None, 0
+            for it in h.lazy.items:
+                if it[-1] != self.rank:
+                    continue
+                if it[0] == "blk":
+                    v = it[1].value
+                else:
+                    _k, a1, a2, s1, s2, t1, t2, _r = it
+                    v = self.local.call("bop", "tensordot", a1.value, a2.value, s1, s2, t1, t2, axes=1)
+                acc = v if acc is None else self.local.call("bop", "add", acc, v, h.shape, h.shape, False, False, axes=None)
+                count += 1
+            partial[h.hid] = acc
+            borrowed[h.hid] = count == 1 and any(it[0] == "blk" and it[-1] == self.rank for it in h.lazy.items)
+        self.backend.flush()
+        # C. sums whose terms live on several ranks: all-reduce (small ones share a buffer)
+        shared, small = [], []
+        for h in alive:
+            ranks = h.lazy.ranks()
+            if len(ranks) == 1:
+                h.value = self.backend.settle(partial[h.hid]) if self.rank == ranks[0] else None
+            elif h.nbytes <= COALESCE_BYTES:
+                small.append(h)
+            else:
+                shared.append(h)
+        if len(small) == 1:
+            shared.append(small.pop())
+        if small:
+            total = sum(int(np.prod(h.shape, dtype=np.int64)) for h in small)
+            buf = self.backend.zeros((total,), np.float64)
+            views, off = [], 0
+            for h in small:
+                view = self.backend.flat_view(buf, off, h.shape)
+                if partial[h.hid] is not None:
+                    self.backend.copy_into(view, self.backend.concrete(partial[h.hid]))
+                views.append(view)
+                off += int(np.prod(h.shape, dtype=np.int64))
+            self.comm.all_reduce_sum(buf)
+            self.stats["all_reduces"] += 1
+            for h, view in zip(small, views):
+                h.value = view
+        for h in shared:
+            acc = partial[h.hid]
+            if acc is None:
+                buf = self.backend.zeros(h.shape, np.float64)
+            elif borrowed[h.hid]:
+                buf = self.backend.clone(acc)           # never reduce in place into somebody's block
+            else:
+                buf = self.backend.concrete(acc)
+            self.comm.all_reduce_sum(buf)
+            self.stats["all_reduces"] += 1
+            h.value = buf
+        for h in alive:
+            h.lazy = None
+
+    # -- n-ary sum over blocks living on several ranks: partial sums + one all-reduce ----------------------
+    def _k_sum_reduce(self, args, kwargs, sysk):
+        if kwargs or not args or not all(isinstance(a, Handle) for a in args):
+            return _NOT_HANDLED
+        if any(h.lazy is not None for h in args):
+            self.flush()
+        owned = [h for h in args if h.home != REPLICATED]
+        if not owned:
+            return _NOT_HANDLED
+        for r in sorted({h.home for h in owned}):
+            if all(h.available_on(r) for h in args):
+                return _NOT_HANDLED                      # everything already sits on one rank
+        first = args[0]
+        if any(h.shape != first.shape or h.dtype != first.dtype for h in args) or first.dtype.kind not in "fiu":
+            return _NOT_HANDLED
+        anchor = owned[0].home                           # replicated addends are counted once, there
+        mine = [h.value for h in args if (h.home if h.home != REPLICATED else anchor) == self.rank]
+        part = self.local.call("sum_reduce", *mine) if mine else self.backend.zeros(first.shape, first.dtype)
+        part = self.backend.concrete(part)
+        self.comm.all_reduce_sum(part)
+        self.stats["all_reduces"] += 1
+        return self._new_handle(REPLICATED, part, first.shape, first.dtype)
+
+    # -- stacked-R qr over blocks living on several ranks: local QR, binary tree, broadcast ---------------
+    def _k_qr(self, args, kwargs, sysk):
+        mode, axis = kwargs.get("mode", "reduced"), kwargs.get("axis")
+        if mode != "r" or len(args) < 2 or axis is None or int(axis) != 0 or not all(isinstance(a, Handle) for a in args):
+            return _NOT_HANDLED
+        if any(h.lazy is not None for h in args):
+            self.flush()
+        owned = [h for h in args if h.home != REPLICATED]
+        if not owned or len({h.home for h in owned}) < 2:
+            return _NOT_HANDLED
+        if any(len(h.shape) != 2 or h.shape[1] != args[0].shape[1] or h.dtype != args[0].dtype for h in args) \
+                or args[0].dtype.kind != "f":
+            return _NOT_HANDLED
+        n, dt = args[0].shape[1], args[0].dtype
+        anchor = owned[0].home
+        where = [h.home if h.home != REPLICATED else anchor for h in args]
+        ranks = sorted(set(where))
+        rows = {r: min(sum(h.shape[0] for h, w in zip(args, where) if w == r), n) for r in ranks}
+        r_local = None
+        if self.rank in ranks:
+            mine = [h.value for h, w in zip(args, where) if w == self.rank]
+            r_local = self.local.call("qr", *mine, mode="r", axis=0) if len(mine) > 1 else self.local.call("qr", mine[0], mode="r")
+        step = 1
+        while step < len(ranks):
+            for idx in range(0, len(ranks), 2 * step):
+                if idx + step >= len(ranks):
+                    continue
+                dst, src = ranks[idx], ranks[idx + step]
+                if self.rank == src:
+                    self.comm.send(self.backend.concrete(r_local), dst)
+                elif self.rank == dst:
+                    other = self.backend.empty((rows[src], n), dt)
+                    self.comm.recv(other, src)
+                    r_local = self.local.call("qr", r_local, other, mode="r", axis=0)
+                rows[dst] = min(rows[dst] + rows[src], n)
+            step *= 2
+        root = ranks[0]
+        out = self.backend.concrete(r_local) if self.rank == root else self.backend.empty((rows[root], n), dt)
+        self.comm.broadcast(out, root)
+        self.stats["broadcasts"] += 1
+        return self._new_handle(REPLICATED, out, (rows[root], n), dt)

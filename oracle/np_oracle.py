@@ -185,7 +185,7 @@ class OracleCompute(object):
     def arg_op(self, op_name, arr, block_slice, other_argoptima=None, other_optima=None):   # :269-283
         if op_name not in ("argmin", "argmax"):
             raise Exception("Unsupported arg op.")
-        local = int(getattr(np, op_name)(arr))
+        local = getattr(np, op_name)(arr)          # np.intp, as in the reference: the result is a NumPy scalar
         best = arr[local]
         if other_optima is not None:
             carried_wins = other_optima < best if op_name == "argmin" else other_optima > best
