@@ -118,6 +118,25 @@ def matmul_blocks_host(seed_a=3, seed_b=4, pinned=True):
     return out["A"], out["B"]
 
 
+_HOST_BLOCKS = {}
+
+
+def host_block(name, i, j, pinned=True):
+    """One 2048 x 2048 block of A or B on the host (same values as matmul_blocks_host), generated on demand
+    and cached -- at N > 1 a rank only ever touches the blocks it owns."""
+    import torch
+    key = (name, i, j)
+    if key not in _HOST_BLOCKS:
+        rng = np.random.default_rng([3 if name == "A" else 4, i, j])
+        arr = rng.standard_normal((BLOCK, BLOCK))
+        if pinned:
+            t = torch.empty((BLOCK, BLOCK), dtype=torch.float64, pin_memory=True)
+            t.numpy()[...] = arr
+            arr = t.numpy()
+        _HOST_BLOCKS[key] = arr
+    return _HOST_BLOCKS[key]
+
+
 def blockarray_from_blocks(host, host_blocks, entries=None, into=None):
     """BlockArray (of the host layers `host`) whose blocks are system.put() from the host dict, `entries`
     (default: all) in order."""
@@ -503,6 +522,72 @@ def sharded_workloads(system, comm, quick):
     return out
 
 
+def api_workloads(host, quick):
+    """cfg1 / cfg3 / cfg4 at N > 1 THROUGH THE PLUGIN API: the reference's BlockArray operators,
+    ArrayApplication.indirect_tsr and glms.newton over SpmdSystem, blocks living on their owners.  Whole-job figures,
+    device-timed, max over ranks (same conventions as sharded_workloads, which calls the drivers directly)."""
+    import torch
+    import torch.distributed as dist
+    system, app = host.system, host.app
+    world, rank = system.world_size, system.rank
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = {}
+
+    def timed(fn, iters):
+        fn()
+        times = []
+        for _ in range(iters):
+            system.synchronize()
+            dist.barrier()
+            t = torch.tensor([cuda_time(fn, torch.cuda.synchronize)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+        return float(np.median(times))
+
+    def distributed(shape, block_shape, fill):
+        ba = host.blockarray(shape, block_shape, "float64")
+        gshape = ba.grid.grid_shape
+        for entry in ba.grid.get_entry_iterator():
+            bshape = ba.grid.get_block_shape(entry)
+            mine = system.owner(entry, gshape) == rank
+            ba.blocks[entry].oid = system.put_at(fill(bshape) if mine else None, entry, gshape, shape=bshape, dtype=np.float64)
+        return ba
+
+    n, G = 100_000_000, 8
+    U = distributed((n,), (n // G,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
+    V = distributed((n,), (n // G,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
+    t = timed(lambda: (host.launch(U + V), torch.cuda.synchronize()), 5 if quick else 20)
+    out["bop_add_api"] = {"value": 24.0 * n / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
+                          "workload": "BlockArray.__add__ of two 1e8-element float64 arrays, 8 blocks over %d GPU(s) through "
+                                      "SpmdSystem (shard-local, no exchange)" % world}
+    del U, V
+
+    m, ncol = 16_777_216, 128
+    X = distributed((m, ncol), (m // G, ncol), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
+    flops_r = 2.0 * m * ncol ** 2 - 2.0 * ncol ** 3 / 3.0
+    t = timed(lambda: (host.launch(app.indirect_tsr(X)), torch.cuda.synchronize()), 2 if quick else 3)
+    out["tsqr_r_api"] = {"value": flops_r / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
+                         "workload": "ArrayApplication.indirect_tsr on 16777216 x 128 float64, 8 row blocks over %d GPU(s): local R "
+                                     "per block, stacked-R qr as a binary tree over the ranks, R replicated" % world}
+    del X
+    torch.cuda.empty_cache()
+
+    N, d = 11_000_000, 28
+    X = distributed((N, d), (N // G, d), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
+    y = distributed((N,), (N // G,), lambda s: (torch.rand(s, dtype=torch.float64, device=dev) < 0.5).to(torch.float64))
+    model = host.logistic_model()
+    iters = 2 if quick else 4
+    t = timed(lambda: (host.launch(host.newton(model, X, y, 1e-300, iters)), torch.cuda.synchronize()), 1 if quick else 2)
+    out["newton_lr_interface_path"] = {
+        "value": t / iters, "unit": "s/iter",
+        "workload": "glms.newton on 11M x 28 float64, 8 row blocks over %d GPU(s) through SpmdSystem: ~15 kernel calls per block "
+                    "per iteration on the block's owner, g and H all-reduced, beta replicated" % world,
+        "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters) / 1e9}
+    del X, y
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_large(args):
     """BASELINE.json configs[4]: float64 65536 x 65536 @ 65536 x 65536, 8 x 8 grid of 8192 x 8192 blocks
     (34.4 GB per operand, 103 GB resident).  Blocks are generated on the device, block by block (seeded);
@@ -613,9 +698,11 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- inputs (host, pinned) -----------------------------------------------------------------------
-    a_host, b_host = matmul_blocks_host(pinned=True)
-
+    from nums_b200 import reference_compat
+    api_path = world == 1 or (reference_compat.available() and not args.mirror and not args.summa_driver)
+    summa = packed = None
     if world == 1:
+        a_host, b_host = matmul_blocks_host(pinned=True)
         from nums_b200.host import HostLayers
         host = HostLayers(prefer_reference=not args.mirror)
         system = host.system            # (a ReferenceCudaSystem when the reference's host layers are driving)
@@ -641,7 +728,42 @@ def run_gpu(args):
             return c.get() if reference_get else host.get(c)
         parallelism = ("1 GPU; host layers = %s; BlockArray.__matmul__ -> _tensordot issues 512 tensordot + 448 add kernel "
                        "calls, deferred by CudaSystem into one grouped DMMA launch per step" % host.description)
+    elif api_path:
+        # N > 1 through the plugin API: every rank runs the reference's BlockArray.__matmul__ over SpmdSystem
+        # (nums_b200/spmd.py); blocks enter on their owners (put_at), operand copies are evicted before every step
+        # so that each product pays for its exchange
+        from nums_b200.host import HostLayers
+        host = HostLayers()
+        system = host.system
+        grid_shape = (GRID, GRID)
+
+        def distributed_operand(name):
+            ba = host.blockarray((N_MATMUL, N_MATMUL), (BLOCK, BLOCK), "float64")
+            for entry in ba.grid.get_entry_iterator():
+                mine = system.owner(entry, grid_shape) == rank
+                ba.blocks[entry].oid = system.put_at(host_block(name, *entry) if mine else None, entry, grid_shape,
+                                                     shape=(BLOCK, BLOCK), dtype=np.float64)
+            return ba
+        A, B = distributed_operand("A"), distributed_operand("B")
+
+        def step_resident():
+            system.evict_copies()
+            c = A @ B
+            system.flush()
+            return c
+
+        def step_e2e(reference_get=False):
+            a, b = distributed_operand("A"), distributed_operand("B")
+            c = a @ b
+            return system.get_owned([c.blocks[e].oid for e in c.grid.get_entry_iterator()])
+        pr, pc = system.device_grid
+        parallelism = ("%d GPUs, one process each; host layers = %s over SpmdSystem: every rank runs BlockArray.__matmul__ "
+                       "(512 tensordot + 448 add kernel calls), C(i,j) is computed on rank (i mod %d)*%d + (j mod %d), remote "
+                       "A(i,k) / B(k,j) blocks are exchanged in one batched NCCL point-to-point transfer per product (cached "
+                       "copies evicted before every step) and each rank contracts its blocks in one grouped DMMA launch"
+                       % (world, host.description, pr, pc, pc))
     else:
+        a_host, b_host = matmul_blocks_host(pinned=True)
         system = CudaSystem(rank=rank, world_size=world)
         system.init()
         pr, pc = multi_gpu.device_grid(world)
@@ -695,7 +817,7 @@ def run_gpu(args):
     seconds = float(elapsed.item())
     value = FLOPS_PER_STEP * args.steps / seconds / 1e12
 
-    if world > 1 and os.environ.get("NUMS_SUMMA_TRACE"):
+    if summa is not None and os.environ.get("NUMS_SUMMA_TRACE"):
         summa.trace = []
         t_start = torch.cuda.Event(enable_timing=True)
         t_start.record()
@@ -733,27 +855,35 @@ def run_gpu(args):
 
     # ---- parity spot check of this run's output (rank 0): one C block against NumPy on the host ------
     verified = None
-    if rank == 0:
-        if world == 1:
-            c_dev = system.get((A @ B).blocks[0, 0].oid)
-        else:
-            c_all = summa.run(packed)
-            key = sorted(c_all)[0]
-            c_dev = system.get(c_all[key])
-        i, j = (0, 0) if world == 1 else key
+    if api_path:
+        c_dev = system.get((A @ B).blocks[0, 0].oid)        # at N > 1 a broadcast from the block's home: all ranks call it
+        if rank == 0:
+            ref = np.zeros((BLOCK, BLOCK))
+            for k in range(GRID):
+                ref += host_block("A", 0, k, pinned=False) @ host_block("B", k, 0, pinned=False)
+            verified = float(np.linalg.norm(c_dev - ref) / np.linalg.norm(ref))
+    elif rank == 0:
+        c_all = summa.run(packed)
+        i, j = key = sorted(c_all)[0]
+        c_dev = system.get(c_all[key])
         ref = np.zeros((BLOCK, BLOCK))
         for k in range(GRID):
             ref += a_host[(i, k)] @ b_host[(k, j)]
         verified = float(np.linalg.norm(c_dev - ref) / np.linalg.norm(ref))
-    elif world > 1:
+    else:
         summa.run(packed)              # collective: every rank takes part in the verification pass
     sync_all()
 
     sharded = None
     if world > 1 and not args.skip_workloads:
-        del packed
+        packed = None
+        if api_path:
+            del A, B
         torch.cuda.empty_cache()
-        sharded = sharded_workloads(system, comm, quick=args.quick)   # collective: all ranks
+        raw_system = system.local if api_path else system
+        sharded = sharded_workloads(raw_system, comm, quick=args.quick)   # collective: all ranks
+        if api_path:
+            sharded.update(api_workloads(host, quick=args.quick))
 
     if rank != 0:
         if world > 1:
@@ -858,9 +988,13 @@ def run_gpu(args):
                    "l2_policy": "inputs (2 x 2.1 GB) and output (2.1 GB) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "TFLOP/s",
                 "h2d_bytes_per_step": 2 * bytes_matrix, "d2h_bytes_per_step": bytes_matrix, "steps": e2e_steps,
-                "what": "pinned host blocks -> system.put (async, upload stream) -> A @ B through the block kernel interface "
-                        "(deferred, launched in groups as operands land) -> CudaSystem.get_assembled on the host (block rows "
-                        "drained on a download stream); wall clock, host<->device copies inside",
+                "what": ("pinned host blocks -> system.put (async, upload stream) -> A @ B through the block kernel interface "
+                         "(deferred, launched in groups as operands land) -> CudaSystem.get_assembled on the host (block rows "
+                         "drained on a download stream); wall clock, host<->device copies inside") if world == 1 else
+                        ("every rank: pinned host blocks it owns -> put_at (async upload) -> BlockArray.__matmul__ over SpmdSystem "
+                         "(exchange + grouped launch) -> get_owned: the C blocks it owns back to its host; wall clock, "
+                         "host<->device copies inside, max over ranks") if api_path else
+                        "every rank: put of its blocks -> SummaMatmul driver -> get of its C blocks; wall clock, max over ranks",
                 "through_reference_BlockArray_get": e2e_blockarray_get},
         "gpu_launches": int(launches),
         "parity_check": {"what": "one 2048x2048 block of C vs NumPy on the host (relative Frobenius error)",
@@ -895,6 +1029,8 @@ def main():
     ap.add_argument("--skip-workloads", action="store_true", help="only the headline matmul")
     ap.add_argument("--quick", action="store_true", help="fewer repetitions of the secondary workloads")
     ap.add_argument("--large", action="store_true", help="config 5 instead: 65536^2 matmul (one-off record run)")
+    ap.add_argument("--summa-driver", action="store_true",
+                    help="N > 1: the hand-called SummaMatmul driver (round 1) instead of BlockArray.__matmul__ over SpmdSystem")
     ap.add_argument("--mirror", action="store_true", help="drive nums_b200.blocks even when the reference's host layers are installed")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -28,8 +28,7 @@ class HostLayers(object):
             from nums.core.storage.storage import ArrayGrid
             from nums.core.systems.filesystem import FileSystem
             if system is None:
-                system = reference_compat.cuda_system_class()(**system_kwargs)
-                system.init()
+                system = reference_compat.cuda_system(**system_kwargs)    # SpmdSystem under torchrun
             self.system = system
             self.app = ArrayApplication(system=system, filesystem=FileSystem(system))
             self.BlockArray, self.ArrayGrid = BlockArray, ArrayGrid

@@ -467,21 +467,30 @@ class SpmdSystem(object):
         shape, dt = self.backend.meta(block)
         return self._new_handle(REPLICATED, block, shape, dt)
 
-    def put_at(self, value, grid_entry, grid_shape):
-        """``put`` for callers that know where the block belongs (the reference's ``put`` carries no placement
-        information, systems.py:94-95, so plain ``put`` replicates): only ``owner(grid_entry, grid_shape)``
-        uploads ``value``; the other ranks may pass ``None`` or an array of the same shape and dtype (ignored)
-        plus, when they pass ``None``, must call with ``like=(shape, dtype)`` semantics via ``value`` being a
-        ``(shape, dtype)`` tuple."""
+    def put_at(self, value, grid_entry, grid_shape, shape=None, dtype=None):
+        """``put`` for callers that know where the block belongs.  The reference's ``put`` carries no placement
+        information (systems.py:94-95), so plain ``put`` replicates; here only ``owner(grid_entry, grid_shape)``
+        uploads ``value`` (a host array or an existing device block).  The other ranks pass ``value=None`` with
+        ``shape`` and ``dtype`` (or the same array, which is then ignored)."""
         home = self.owner(tuple(grid_entry), tuple(grid_shape))
-        if isinstance(value, tuple) and len(value) == 2 and not hasattr(value, "shape"):
-            shape, dt = value
-            assert self.rank != home, "the owner must pass the data"
-            return self._new_handle(home, None, shape, np.dtype(dt))
-        arr = value
-        shape, dt = tuple(arr.shape), (np.dtype(arr.dtype) if isinstance(arr, np.ndarray) else self.backend.meta(arr)[1])
-        block = self.local.put(arr) if self.rank == home else None
-        return self._new_handle(home, block, shape, dt)
+        if value is not None:
+            vshape, vdtype = self.backend.meta(value) if self.backend.is_block(value) else (np.shape(value), np.asarray(value).dtype)
+            shape = vshape if shape is None else shape
+            dtype = vdtype if dtype is None else dtype
+        elif shape is None or dtype is None:
+            raise ValueError("put_at: ranks that do not own the block must give shape and dtype")
+        if self.rank == home and value is None:
+            raise ValueError("put_at: rank %d owns block %s and must pass its data" % (home, (grid_entry,)))
+        block = self.local.put(value) if self.rank == home else None
+        return self._new_handle(home, block, shape, np.dtype(dtype))
+
+    def get_owned(self, oids):
+        """{position in ``oids``: host array} for the blocks that live on THIS rank (no exchange): how a
+        distributed result is drained to the hosts that own it, one PCIe link per GPU."""
+        self.flush()
+        mine = [(i, h) for i, h in enumerate(oids) if isinstance(h, Handle) and h.home in (self.rank, REPLICATED)]
+        values = self.local.get([h.value for _i, h in mine])
+        return {i: v for (i, _h), v in zip(mine, values)}
 
     def evict_copies(self):
         """Forget every cached copy of a remote block (the blocks themselves stay at home).  Operand copies
