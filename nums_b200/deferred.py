@@ -46,8 +46,13 @@ def _dmma_ok(t, ld):
     return t.dtype == torch.float64 and t.data_ptr() % 16 == 0 and ld % 2 == 0
 
 
-def plan_launch_groups(needs, done, max_groups):
+def plan_launch_groups(needs, done, max_groups, policy="even"):
     """Pure planning step of ``ContractionQueue._launch_groups``.
+
+    ``policy`` = "even": neighbouring runs are merged evenly (operands streaming in over PCIe at a rate
+    comparable to the GEMM's); "head": the first run alone, everything else in ONE launch -- for operands
+    pulled over NVLink (nums_b200.spmd.PeerExchange), which all arrive within the first launch's run time,
+    so a second split would only add a partial wave.
 
     ``needs[i]`` is ``None`` or ``(sequence number, event)`` of the latest upload contraction i reads;
     uploads up to sequence number ``done`` have already been waited for.  Returns a list of
@@ -64,10 +69,15 @@ def plan_launch_groups(needs, done, max_groups):
             runs[-1].append(i)
         else:
             runs.append([i])
-    merge = max(1, -(-len(runs) // max_groups))
+    if policy == "head" and len(runs) > 2:
+        first = 1 if seq_of[runs[0][0]] else 2      # run 0 may be "needs nothing": take the first waiting run too
+        chunks = [runs[:first], runs[first:]] if len(runs) > first else [runs]
+    else:
+        merge = max(1, -(-len(runs) // max_groups))
+        chunks = [runs[lo:lo + merge] for lo in range(0, len(runs), merge)]
     out = []
-    for lo in range(0, len(runs), merge):
-        idx = [i for run in runs[lo:lo + merge] for i in run]
+    for chunk in chunks:
+        idx = [i for run in chunk for i in run]
         tags = [needs[i] for i in idx if seq_of[i]]
         out.append((idx, max(tags, key=lambda t: t[0]) if tags else None))
     return out
@@ -79,6 +89,7 @@ class ContractionQueue(object):
         self._pending = []   # weak references to unmaterialised contractions, in creation order
         self.flushes = 0
         self.enabled = True
+        self.group_policy = "even"       # how a flush is cut into launches, see plan_launch_groups
         self.materialized_seen = False   # deferred handles exist somewhere: keep resolving arguments
 
     # -- building -------------------------------------------------------------------------------
@@ -179,7 +190,8 @@ class ContractionQueue(object):
         single launch."""
         done = cuda_compute._Transfers.awaited.get(cuda_compute._stream_unordered(), 0)
         needs = [self._need(d) for d in group]
-        return [([group[i] for i in idx], upto) for idx, upto in plan_launch_groups(needs, done, MAX_GROUPS)]
+        return [([group[i] for i in idx], upto)
+                for idx, upto in plan_launch_groups(needs, done, MAX_GROUPS, self.group_policy)]
 
     def _launch(self, ta, tb, group, upto, mark_done):
         if upto is not None:

@@ -292,6 +292,107 @@ def infer_result(name, args, kwargs, meta_of):
     return None
 
 
+class PeerExchange(object):
+    """Bulk operand movement over NVLink peer memory, driven by the copy engines (GPU back end only).
+
+    NCCL point-to-point transfers occupy SMs next to the DMMA kernel and run as one un-overlapped phase; here
+    the exchange of a flush is a set of *pulls* instead: every rank stages the float64 blocks it has to serve
+    into a symmetric-memory arena (``torch.distributed._symmetric_memory``: the same allocation on every rank,
+    mapped into every peer's address space; the staging copy is device-to-device and costs ~10 us per 32 MB
+    block), two device-side barriers bracket the staging (nobody still reads the previous contents / every
+    arena is filled), and each destination then copies its operands straight out of the owners' arenas on the
+    upload stream.  A pulled block looks exactly like an asynchronously uploaded one (``_nums_ready`` tag,
+    cuda_compute._Transfers), so CudaSystem's deferred-contraction flush starts the grouped GEMM of the first
+    result blocks as soon as THEIR operands have landed and overlaps the rest of the exchange with it.
+    No SM is taken from the GEMM and no rank waits for another beyond the two barriers."""
+
+    MIN_BYTES = 1 << 20
+
+    def __init__(self, comm):
+        self.comm = comm
+        self.capacity = 0          # float64 elements
+        self.buf = None
+        self.handle = None
+        self.failed = False
+
+    def usable(self, moves):
+        if self.failed or not moves:
+            return False
+        f64 = np.dtype(np.float64)
+        return all(h.dtype == f64 for h, _dst in moves) and sum(h.nbytes for h, _dst in moves) >= self.MIN_BYTES
+
+    def _ensure(self, elements):
+        """Collective: every rank calls with the same ``elements``."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if elements <= self.capacity:
+            return True
+        ok = 1
+        try:
+            cap = max(int(elements * 1.25), 1 << 20)
+            buf = symm.empty(cap, dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+            handle = symm.rendezvous(buf, dist.group.WORLD)
+        except Exception as exc:  # noqa: BLE001 -- any failure selects the NCCL transfers
+            import sys
+            sys.stderr.write("[nums_b200] symmetric-memory arena unavailable (%s: %s); using NCCL point-to-point\n"
+                             % (type(exc).__name__, exc))
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # all ranks take the same path
+        if int(flag.item()) != 1:
+            self.failed = True
+            return False
+        self.buf, self.handle, self.capacity = buf, handle, cap
+        return True
+
+    def run(self, moves, rank, backend):
+        """``moves`` = [(handle, dst)] (identical on all ranks, none available on its dst yet).  Returns False
+        if the exchange has to go through NCCL instead."""
+        import torch
+        from nums_b200 import cuda_compute as cc
+        # arena layout per serving rank: every distinct block once, 16-element aligned
+        offsets, fill = {}, {}
+        for h, _dst in moves:
+            if h.hid not in offsets:
+                off = fill.get(h.home, 0)
+                offsets[h.hid] = off
+                fill[h.home] = off + (-(-int(np.prod(h.shape, dtype=np.int64)) // 16)) * 16
+        if not self._ensure(max(fill.values())):
+            return False
+        home = torch.cuda.current_stream()
+        cc.await_uploads(home)
+        self.handle.barrier(channel=0)                       # nobody is still pulling the previous contents
+        staged = set()
+        for h, _dst in moves:
+            if h.home == rank and h.hid not in staged:
+                staged.add(h.hid)
+                n = int(np.prod(h.shape, dtype=np.int64))
+                src = backend.settle(h.value)
+                self.buf[offsets[h.hid]:offsets[h.hid] + n].view(h.shape).copy_(src)   # D2D placement copy (plumbing)
+        self.handle.barrier(channel=1)                       # every arena is filled
+        ready = torch.cuda.Event()
+        ready.record(home)
+        up = cc._upload_stream()
+        up.wait_event(ready)
+        device = torch.device("cuda", torch.cuda.current_device())
+        for h, dst in moves:
+            if dst != rank:
+                continue
+            remote = self.handle.get_buffer(h.home, h.shape, torch.float64, offsets[h.hid])
+            with torch.cuda.stream(up):
+                dev = torch.empty(h.shape, dtype=torch.float64, device=device)
+                dev.copy_(remote, non_blocking=True)
+            dev.record_stream(home)
+            event = torch.cuda.Event()
+            event.record(up)
+            cc._Transfers.seq += 1
+            cc._Transfers.last_event = event
+            dev._nums_ready = (cc._Transfers.seq, event)
+            h.value = dev
+        return True
+
+
 class SpmdSystem(object):
     """See the module docstring.  ``local`` executes kernels on this rank; ``comm`` is a ``multi_gpu.Comm``."""
 
@@ -314,7 +415,12 @@ class SpmdSystem(object):
         self._lazies = []
         self._copied = weakref.WeakSet()      # handles with cached copies away from home
         self.stats = {"moves": 0, "moved_bytes": 0, "all_reduces": 0, "broadcasts": 0, "meta_broadcasts": 0,
-                      "executed": 0, "skipped": 0, "replicated": 0, "flushes": 0}
+                      "executed": 0, "skipped": 0, "replicated": 0, "flushes": 0, "peer_exchanges": 0}
+        self._peer = None
+        if (isinstance(self.backend, _TorchBackend) and self.world_size > 1
+                and os.environ.get("NUMS_SPMD_PEER", "1") != "0"):
+            self._peer = PeerExchange(self.comm)
+            local.contractions.group_policy = "head"     # see deferred.plan_launch_groups
 
     # -- lifecycle ------------------------------------------------------------------------------------
     def init(self):
@@ -547,6 +653,14 @@ class SpmdSystem(object):
         """[(handle, dst)]: make each block available on ``dst`` (cached there).  One batched exchange."""
         moves = [(h, dst) for h, dst in moves if not h.available_on(dst)]
         if not moves:
+            return
+        if self._peer is not None and self._peer.usable(moves) and self._peer.run(moves, self.rank, self.backend):
+            for h, dst in moves:
+                h.copies = tuple(h.copies) + (dst,)
+                self._copied.add(h)
+                self.stats["moves"] += 1
+                self.stats["moved_bytes"] += h.nbytes
+            self.stats["peer_exchanges"] += 1
             return
         sends, recvs = [], []
         for h, dst in moves:
