@@ -817,6 +817,19 @@ def run_gpu(args):
     seconds = float(elapsed.item())
     value = FLOPS_PER_STEP * args.steps / seconds / 1e12
 
+    if os.environ.get("NUMS_TRACE") == "1":
+        from nums_b200 import trace
+        trace.report()
+        host_ms = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            step_resident()
+            host_ms.append((time.perf_counter() - t0) * 1e3)
+        rows = trace.report()
+        if rank == 0:
+            sys.stderr.write("TRACE host ms per step_resident call: %s\n" % ", ".join("%.1f" % m for m in host_ms))
+            for label, t, dt, host_t in rows:
+                sys.stderr.write("TRACE %9.3f ms (+%8.3f) host %8.1f  %s\n" % (t, dt, host_t, label))
     if summa is not None and os.environ.get("NUMS_SUMMA_TRACE"):
         summa.trace = []
         t_start = torch.cuda.Event(enable_timing=True)

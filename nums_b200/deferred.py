@@ -52,7 +52,8 @@ def plan_launch_groups(needs, done, max_groups, policy="even"):
     ``policy`` = "even": neighbouring runs are merged evenly (operands streaming in over PCIe at a rate
     comparable to the GEMM's); "head": the first run alone, everything else in ONE launch -- for operands
     pulled over NVLink (nums_b200.spmd.PeerExchange), which all arrive within the first launch's run time,
-    so a second split would only add a partial wave.
+    so a second split would only add a partial wave; "single": one launch that waits for everything
+    (the caller cuts the work itself, nums_b200.spmd.SpmdSystem.flush).
 
     ``needs[i]`` is ``None`` or ``(sequence number, event)`` of the latest upload contraction i reads;
     uploads up to sequence number ``done`` have already been waited for.  Returns a list of
@@ -69,7 +70,9 @@ def plan_launch_groups(needs, done, max_groups, policy="even"):
             runs[-1].append(i)
         else:
             runs.append([i])
-    if policy == "head" and len(runs) > 2:
+    if policy == "single":
+        chunks = [runs]
+    elif policy == "head" and len(runs) > 2:
         first = 1 if seq_of[runs[0][0]] else 2      # run 0 may be "needs nothing": take the first waiting run too
         chunks = [runs[:first], runs[first:]] if len(runs) > first else [runs]
     else:
@@ -112,6 +115,34 @@ class ContractionQueue(object):
         if not (_dmma_ok(A, lda) and _dmma_ok(B, ldb)):
             return None
         return self._register(DeferredContraction(((A, lda, B, ldb, k, a1, a2),), (m, n), (bool(ta), bool(tb))))
+
+    def build(self, terms, shape):
+        """One deferred contraction sum_t np.tensordot(a1_t, a2_t, 1) from a whole term list
+        [(a1, a2, a1_shape, a2_shape, a1_T, a2_T)] (what a dot / add chain would have built call by call);
+        None if any term is ineligible or the terms do not share one (trans_a, trans_b) class."""
+        if not self.enabled or not terms:
+            return None
+        out, flags = [], None
+        m, n = shape
+        for a1, a2, a1_shape, a2_shape, a1_T, a2_T in terms:
+            if not (isinstance(a1, torch.Tensor) and isinstance(a2, torch.Tensor)) \
+                    or a1.dtype != torch.float64 or a2.dtype != torch.float64 or len(a1_shape) != 2 or len(a2_shape) != 2:
+                return None
+            k = int(a1_shape[1])
+            if (int(a1_shape[0]), int(a2_shape[1])) != (m, n) or k != int(a2_shape[0]) or m < MIN_EXTENT or n < MIN_EXTENT or k < 1:
+                return None
+            x = cuda_compute._operand(a1, a1_shape, a1_T)
+            y = cuda_compute._operand(a2, a2_shape, a2_T)
+            A, ta, lda = cuda_compute._as_matrix(x, m, k)
+            B, tb, ldb = cuda_compute._as_matrix(y, k, n)
+            if not (_dmma_ok(A, lda) and _dmma_ok(B, ldb)):
+                return None
+            if flags is None:
+                flags = (bool(ta), bool(tb))
+            elif flags != (bool(ta), bool(tb)):
+                return None
+            out.append((A, lda, B, ldb, k, a1, a2))
+        return self._register(DeferredContraction(tuple(out), (m, n), flags))
 
     def add(self, x, y, x_shape, y_shape, x_T, y_T):
         """Lazy x + y when at least one side is an unmaterialised contraction of the same shape."""
@@ -216,8 +247,11 @@ class ContractionQueue(object):
                 tm.A, tm.B, tm.lda, tm.ldb, tm.k = A.data_ptr(), B.data_ptr(), lda, ldb, k
                 cursor += 1
         device = group[0].value.device
+        from nums_b200 import trace
+        trace.mark("grouped gemm: start (%d blocks, %d terms)" % (len(group), nterms))
         LIB.call_ws(LIB.dll.nums_gemm_grouped, device,
                     ((_lib.F64, int(ta), int(tb), len(group), problems, nterms, terms), (stream,)))
+        trace.mark("grouped gemm: end")
         if mark_done:
             # lets get_assembled start the D2H of these blocks while later groups still compute
             done = torch.cuda.Event()

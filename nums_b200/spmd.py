@@ -43,6 +43,7 @@ import weakref
 import numpy as np
 
 REPLICATED = -1
+_F64 = np.dtype(np.float64)
 _NOT_HANDLED = object()
 _BOP_PARAMS = ("op", "a1", "a2", "a1_shape", "a2_shape", "a1_T", "a2_T", "axes")
 LAZY_MIN_EXTENT = 64            # same eligibility as CudaSystem's deferred contractions (deferred.py)
@@ -62,6 +63,13 @@ class Handle(object):
         self.dtype = np.dtype(dtype)
         self.copies = ()                  # ranks (besides home) that hold a cached copy
         self.lazy = None                  # _Lazy while the value is still an unevaluated sum
+
+    @classmethod
+    def _make(cls, hid, home, value, shape, dtype):
+        """Constructor for an already normalised ``shape`` (tuple of int) / ``dtype`` (np.dtype)."""
+        h = cls.__new__(cls)
+        h.hid, h.home, h.value, h.shape, h.dtype, h.copies, h.lazy = hid, home, value, shape, dtype, (), None
+        return h
 
     def available_on(self, rank):
         return self.home == REPLICATED or self.home == rank or rank in self.copies
@@ -314,6 +322,7 @@ class PeerExchange(object):
         self.buf = None
         self.handle = None
         self.failed = False
+        self.pulled = False        # set by run(): pulls of this exchange may still be in flight
 
     def usable(self, moves):
         if self.failed or not moves:
@@ -360,8 +369,10 @@ class PeerExchange(object):
                 fill[h.home] = off + (-(-int(np.prod(h.shape, dtype=np.int64)) // 16)) * 16
         if not self._ensure(max(fill.values())):
             return False
+        from nums_b200 import trace
         home = torch.cuda.current_stream()
         cc.await_uploads(home)
+        trace.mark("exchange: begin")
         self.handle.barrier(channel=0)                       # nobody is still pulling the previous contents
         staged = set()
         for h, _dst in moves:
@@ -370,7 +381,9 @@ class PeerExchange(object):
                 n = int(np.prod(h.shape, dtype=np.int64))
                 src = backend.settle(h.value)
                 self.buf[offsets[h.hid]:offsets[h.hid] + n].view(h.shape).copy_(src)   # D2D placement copy (plumbing)
+        trace.mark("exchange: staged")
         self.handle.barrier(channel=1)                       # every arena is filled
+        trace.mark("exchange: barrier 1")
         ready = torch.cuda.Event()
         ready.record(home)
         up = cc._upload_stream()
@@ -390,6 +403,8 @@ class PeerExchange(object):
             cc._Transfers.last_event = event
             dev._nums_ready = (cc._Transfers.seq, event)
             h.value = dev
+        trace.mark("exchange: pulls done", up)
+        self.pulled = True
         return True
 
 
@@ -412,6 +427,7 @@ class SpmdSystem(object):
         self.rng_cls = getattr(local, "rng_cls", None)
         self._registered = set()
         self._next = 0
+        self._owners = {}
         self._lazies = []
         self._copied = weakref.WeakSet()      # handles with cached copies away from home
         self.stats = {"moves": 0, "moved_bytes": 0, "all_reduces": 0, "broadcasts": 0, "meta_broadcasts": 0,
@@ -420,7 +436,7 @@ class SpmdSystem(object):
         if (isinstance(self.backend, _TorchBackend) and self.world_size > 1
                 and os.environ.get("NUMS_SPMD_PEER", "1") != "0"):
             self._peer = PeerExchange(self.comm)
-            local.contractions.group_policy = "head"     # see deferred.plan_launch_groups
+            local.contractions.group_policy = "single"   # flush() below cuts launches along k itself
 
     # -- lifecycle ------------------------------------------------------------------------------------
     def init(self):
@@ -489,19 +505,30 @@ class SpmdSystem(object):
         do not decide it."""
         if self.world_size == 1 or len(grid_entry) == 0:
             return 0
+        key = (grid_entry, grid_shape)
+        hit = self._owners.get(key)
+        if hit is not None:
+            return hit
         long_axes = [i for i, g in enumerate(grid_shape) if g > 1]
         if self.placement == "flat" or len(long_axes) <= 1:
-            return int(np.ravel_multi_index(tuple(grid_entry), tuple(grid_shape))) % self.world_size
-        pr, pc = self.device_grid
-        a0, a1 = long_axes[0], long_axes[1]
-        return (grid_entry[a0] % pr) * pc + (grid_entry[a1] % pc)
+            out = int(np.ravel_multi_index(tuple(grid_entry), tuple(grid_shape))) % self.world_size
+        else:
+            pr, pc = self.device_grid
+            a0, a1 = long_axes[0], long_axes[1]
+            out = int((grid_entry[a0] % pr) * pc + (grid_entry[a1] % pc))
+        if len(self._owners) < (1 << 16):
+            self._owners[key] = out
+        return out
 
     def _hint(self, sysk, rank=None):
         if rank is not None:
             return rank % self.world_size
         if not sysk or "grid_entry" not in sysk:
             return None
-        return self.owner(tuple(sysk["grid_entry"]), tuple(sysk["grid_shape"]))
+        entry, shape = sysk["grid_entry"], sysk["grid_shape"]
+        if entry.__class__ is not tuple or shape.__class__ is not tuple:
+            entry, shape = tuple(int(e) for e in entry), tuple(int(g) for g in shape)
+        return self.owner(entry, shape)
 
     def _exec_rank(self, handles, sysk, single, rank=None):
         owned = [h for h in handles if h.home != REPLICATED]
@@ -679,8 +706,7 @@ class SpmdSystem(object):
 
     # -- dispatch -------------------------------------------------------------------------------------
     def call(self, name, *args, **kwargs):
-        kwargs = dict(kwargs)
-        sysk = kwargs.pop("syskwargs", None)
+        sysk = kwargs.pop("syskwargs", None)          # (**kwargs is a fresh dict per call)
         rank = kwargs.pop("_rank", None)
         if name == "touch":
             self.flush()
@@ -737,8 +763,10 @@ class SpmdSystem(object):
     # -- lazily summed contractions ---------------------------------------------------------------------
     def _lazy_handle(self, items, hint, shape, dtype):
         lazy = _Lazy(items, hint)
-        ranks = lazy.ranks()
-        h = self._new_handle(ranks[0] if len(ranks) == 1 else REPLICATED, None, shape, dtype)
+        first = items[0][-1]
+        single = all(it[-1] == first for it in items)
+        self._next += 1
+        h = Handle._make(self._next, first if single else REPLICATED, None, shape, dtype)
         h.lazy = lazy
         self._lazies.append(weakref.ref(h))
         return h
@@ -752,42 +780,45 @@ class SpmdSystem(object):
         return hint if hint is not None else (a1.home if a1.home != REPLICATED else a2.home)
 
     def _k_bop(self, args, kwargs, sysk):
-        bound = dict(zip(_BOP_PARAMS, args))
-        bound.update(kwargs)
-        if len(bound) != len(_BOP_PARAMS):
+        if len(args) == 7 and len(kwargs) == 1 and "axes" in kwargs:      # how Block.bop calls (base.py:220-231)
+            op, a1, a2, s1, s2, t1, t2 = args
+            axes = kwargs["axes"]
+        else:
+            bound = dict(zip(_BOP_PARAMS, args))
+            bound.update(kwargs)
+            if len(bound) != len(_BOP_PARAMS):
+                return _NOT_HANDLED
+            op, a1, a2, s1, s2, t1, t2, axes = (bound[k] for k in _BOP_PARAMS)
+        if a1.__class__ is not Handle or a2.__class__ is not Handle:
             return _NOT_HANDLED
-        op, a1, a2 = bound["op"], bound["a1"], bound["a2"]
-        if not (isinstance(a1, Handle) and isinstance(a2, Handle)):
-            return _NOT_HANDLED
-        f64 = np.dtype(np.float64)
         if op == "tensordot":
-            s1, s2 = tuple(bound["a1_shape"]), tuple(bound["a2_shape"])
-            if (a1.lazy is None and a2.lazy is None and bound["axes"] == 1 and len(s1) == 2 and len(s2) == 2
-                    and a1.dtype == f64 and a2.dtype == f64 and s1[1] == s2[0]
+            if (axes == 1 and len(s1) == 2 and len(s2) == 2 and a1.lazy is None and a2.lazy is None
+                    and a1.dtype == _F64 and a2.dtype == _F64 and s1[1] == s2[0]
                     and s1[0] >= LAZY_MIN_EXTENT and s2[1] >= LAZY_MIN_EXTENT and s1[1] >= 1):
                 hint = self._hint(sysk)
                 hint = 0 if hint is None else hint
-                item = ("dot", a1, a2, s1, s2, bool(bound["a1_T"]), bool(bound["a2_T"]), self._term_rank(a1, a2, hint))
-                return self._lazy_handle([item], hint, (s1[0], s2[1]), f64)
+                item = ("dot", a1, a2, tuple(s1), tuple(s2), bool(t1), bool(t2), self._term_rank(a1, a2, hint))
+                return self._lazy_handle([item], hint, (int(s1[0]), int(s2[1])), _F64)
             return _NOT_HANDLED
-        if op == "add" and not bound["a1_T"] and not bound["a2_T"] and a1.dtype == f64 and a2.dtype == f64 \
-                and tuple(bound["a1_shape"]) == tuple(bound["a2_shape"]) == a1.shape == a2.shape:
-            hint = self._hint(sysk)
-            if a1.lazy is not None or a2.lazy is not None:
-                lazy_hint = (a1.lazy or a2.lazy).hint
+        if op == "add" and not t1 and not t2 and a1.dtype == _F64 and a2.dtype == _F64 \
+                and tuple(s1) == tuple(s2) == a1.shape == a2.shape:
+            l1, l2 = a1.lazy, a2.lazy
+            if l1 is not None or l2 is not None:
+                lazy_hint = (l1 or l2).hint
                 items = []
-                for h in (a1, a2):
-                    if h.lazy is not None:
-                        items.extend(h.lazy.items)
+                for h, lz in ((a1, l1), (a2, l2)):
+                    if lz is not None:
+                        items.extend(lz.items)
                     else:
                         items.append(("blk", h, h.home if h.home != REPLICATED else lazy_hint))
-                return self._lazy_handle(items, lazy_hint, a1.shape, f64)
+                return self._lazy_handle(items, lazy_hint, a1.shape, _F64)
             if (a1.home != REPLICATED and a2.home != REPLICATED and a1.home != a2.home
                     and not a1.available_on(a2.home) and not a2.available_on(a1.home)):
                 # partial results living on different ranks (the add chains of _tensordot / reduce_axis):
                 # summed where they are and all-reduced, instead of being shipped to one rank one by one
+                hint = self._hint(sysk)
                 items = [("blk", a1, a1.home), ("blk", a2, a2.home)]
-                return self._lazy_handle(items, 0 if hint is None else hint, a1.shape, f64)
+                return self._lazy_handle(items, 0 if hint is None else hint, a1.shape, _F64)
         return _NOT_HANDLED
 
     def flush(self):
@@ -802,22 +833,45 @@ class SpmdSystem(object):
             self.backend.flush()
             return
         self.stats["flushes"] += 1
-        # A. operands that must travel: one batched exchange
+        # A. operands that must travel: one batched exchange.  The operands of every block's FIRST term go
+        #    first, so that a launch over all blocks can start after a fraction of the exchange (see B).
         moves, seen = [], set()
-        for h in alive:
-            for it in h.lazy.items:
-                if it[0] != "dot":
-                    continue
-                for operand in (it[1], it[2]):
-                    key = (operand.hid, it[-1])
-                    if key not in seen and not operand.available_on(it[-1]):
-                        seen.add(key)
-                        moves.append((operand, it[-1]))
+        for first_only in (True, False):
+            for h in alive:
+                dots = [it for it in h.lazy.items if it[0] == "dot"]
+                for it in (dots[:1] if first_only else dots[1:]):
+                    for operand in (it[1], it[2]):
+                        key = (operand.hid, it[-1])
+                        if key not in seen and not operand.available_on(it[-1]):
+                            seen.add(key)
+                            moves.append((operand, it[-1]))
+        if self._peer is not None:
+            self._peer.pulled = False
         self._move_many(moves)
-        # B. every rank evaluates its own terms (CudaSystem defers them into one grouped launch)
-        partial, borrowed = {}, {}
+        overlap = self._peer is not None and self._peer.pulled        # pulls are in flight on the upload stream
+        # B. every rank evaluates its own terms.  CudaSystem defers them into grouped launches whose CTAs keep a
+        #    block's k-chain in registers.  While pulls are in flight the work is cut ALONG k, not by block:
+        #    launch 1 = the first term of every block (waits for those operands only, and -- covering all
+        #    blocks -- fills the machine as evenly as the whole product), launch 2 = all remaining terms
+        #    accumulated onto launch 1's result; by then the rest of the exchange has landed.
+        partial, borrowed, tails = {}, {}, []
+        build = getattr(getattr(self.local, "contractions", None), "build", None)
         for h in alive:
             acc, count = None, 0
+            mine = [it for it in h.lazy.items if it[-1] == self.rank]
+            if build is not None and len(mine) > 1 and all(it[0] == "dot" for it in mine):
+                # the whole k-chain of this block as ONE deferred contraction (no per-term dot / add replay)
+                terms = [(it[1].value, it[2].value, it[3], it[4], it[5], it[6]) for it in mine]
+                if overlap and len(terms) >= 3:
+                    head = build(terms[:1], h.shape)
+                    if head is not None:
+                        partial[h.hid], borrowed[h.hid] = head, False
+                        tails.append((h, head, terms[1:]))
+                        continue
+                acc = build(terms, h.shape)
+                if acc is not None:
+                    partial[h.hid], borrowed[h.hid] = acc, False
+                    continue
             for it in h.lazy.items:
                 if it[-1] != self.rank:
                     continue
@@ -830,7 +884,25 @@ class SpmdSystem(object):
                 count += 1
             partial[h.hid] = acc
             borrowed[h.hid] = count == 1 and any(it[0] == "blk" and it[-1] == self.rank for it in h.lazy.items)
+        # drop the loop's last handles before the local flush: a deferred contraction that something besides
+        # `partial` still references would be launched a second time on its own (see deferred.py)
+        acc = v = head = None
         self.backend.flush()
+        if tails:
+            for h, head, terms in tails:
+                rest = build(terms, h.shape)
+                done = self.backend.settle(head)
+                if rest is None:      # (cannot happen for terms that built once; keep the chain correct anyway)
+                    rest = done
+                    for a1v, a2v, s1, s2, t1, t2 in terms:
+                        dot = self.local.call("bop", "tensordot", a1v, a2v, s1, s2, t1, t2, axes=1)
+                        rest = self.local.call("bop", "add", rest, dot, h.shape, h.shape, False, False, axes=None)
+                    partial[h.hid] = rest
+                else:
+                    partial[h.hid] = self.local.call("bop", "add", rest, done, h.shape, h.shape, False, False, axes=None)
+            rest = done = head = dot = None
+            tails = None
+            self.backend.flush()
         # C. sums whose terms live on several ranks: all-reduce (small ones share a buffer)
         shared, small = [], []
         for h in alive:
