@@ -323,6 +323,9 @@ class PeerExchange(object):
         self.handle = None
         self.failed = False
         self.pulled = False        # set by run(): pulls of this exchange may still be in flight
+        self.stream = None         # high-priority stream for barriers + staging (so they do not queue behind a GEMM)
+        self.slots = {}            # hid -> (weakref to the handle, offset in its home rank's arena): what is staged where
+        self.fill = {}             # rank -> elements used in that rank's arena
 
     def usable(self, moves):
         if self.failed or not moves:
@@ -338,6 +341,10 @@ class PeerExchange(object):
         if elements <= self.capacity:
             return True
         ok = 1
+        if self.buf is not None:
+            # growing replaces the arena: nobody may still be pulling from the old one when it is released
+            torch.cuda.synchronize()
+            dist.barrier()
         try:
             cap = max(int(elements * 1.25), 1 << 20)
             buf = symm.empty(cap, dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
@@ -357,42 +364,77 @@ class PeerExchange(object):
 
     def run(self, moves, rank, backend):
         """``moves`` = [(handle, dst)] (identical on all ranks, none available on its dst yet).  Returns False
-        if the exchange has to go through NCCL instead."""
+        if the exchange has to go through NCCL instead.
+
+        Staged blocks STAY in the arena while their handle lives (blocks are immutable), so serving the same
+        operand again -- every product of a loop over the same matrices -- costs no staging copy and no
+        barrier: the destinations simply pull.  The arena is an append-only log per rank, compacted (reset +
+        re-stage, bracketed by the "nobody is still pulling" barrier) when it fills up.  Every rank tracks
+        every rank's log, from the same global move lists, so offsets never have to be communicated."""
         import torch
         from nums_b200 import cuda_compute as cc
-        # arena layout per serving rank: every distinct block once, 16-element aligned
-        offsets, fill = {}, {}
-        for h, _dst in moves:
-            if h.hid not in offsets:
-                off = fill.get(h.home, 0)
-                offsets[h.hid] = off
-                fill[h.home] = off + (-(-int(np.prod(h.shape, dtype=np.int64)) // 16)) * 16
-        if not self._ensure(max(fill.values())):
-            return False
         from nums_b200 import trace
-        home = torch.cuda.current_stream()
-        cc.await_uploads(home)
-        trace.mark("exchange: begin")
-        self.handle.barrier(channel=0)                       # nobody is still pulling the previous contents
-        staged = set()
+
+        def elements(h):
+            return (-(-int(np.prod(h.shape, dtype=np.int64)) // 16)) * 16        # 128-byte aligned slots
+
+        needed = {}
         for h, _dst in moves:
-            if h.home == rank and h.hid not in staged:
-                staged.add(h.hid)
-                n = int(np.prod(h.shape, dtype=np.int64))
-                src = backend.settle(h.value)
-                self.buf[offsets[h.hid]:offsets[h.hid] + n].view(h.shape).copy_(src)   # D2D placement copy (plumbing)
-        trace.mark("exchange: staged")
-        self.handle.barrier(channel=1)                       # every arena is filled
-        trace.mark("exchange: barrier 1")
-        ready = torch.cuda.Event()
-        ready.record(home)
+            needed.setdefault(h.hid, h)
+        for hid in [hid for hid, (ref, _off) in self.slots.items() if ref() is None]:
+            del self.slots[hid]                                                   # (space comes back at the next reset)
+        fresh = [h for hid, h in needed.items() if hid not in self.slots]
+        reset = False
+        if fresh:
+            fill = dict(self.fill)
+            for h in fresh:
+                fill[h.home] = fill.get(h.home, 0) + elements(h)
+            if max(fill.values()) > self.capacity:
+                reset, fresh, fill = True, list(needed.values()), {}
+                for h in fresh:
+                    fill[h.home] = fill.get(h.home, 0) + elements(h)
+                if not self._ensure(max(fill.values())):
+                    return False
+                self.slots, self.fill = {}, {}
+            for h in fresh:
+                off = self.fill.get(h.home, 0)
+                self.slots[h.hid] = (weakref.ref(h), off)
+                self.fill[h.home] = off + elements(h)
+        home = torch.cuda.current_stream()
         up = cc._upload_stream()
-        up.wait_event(ready)
+        if fresh:
+            if self.stream is None:
+                self.stream = torch.cuda.Stream(priority=-1)
+            side = self.stream
+            # Barriers and staging run on a side stream ordered after everything the compute stream has been
+            # given so far (the producers of the blocks to stage; the launches that consumed earlier pulls), so
+            # the compute stream itself is free to start this flush's first launch on local operands at once.
+            begin = torch.cuda.Event()
+            begin.record(home)
+            side.wait_event(begin)
+            cc.await_uploads(side)
+            with torch.cuda.stream(side):
+                trace.mark("exchange: begin (staging %d blocks%s)" % (len(fresh), ", arena reset" if reset else ""), side)
+                if reset:
+                    self.handle.barrier(channel=0)           # nobody is still pulling the contents about to be overwritten
+                for h in fresh:
+                    if h.home == rank:
+                        n = int(np.prod(h.shape, dtype=np.int64))
+                        off = self.slots[h.hid][1]
+                        src = backend.settle(h.value)
+                        src.record_stream(side)
+                        self.buf[off:off + n].view(h.shape).copy_(src)          # D2D placement copy (plumbing)
+                trace.mark("exchange: staged", side)
+                self.handle.barrier(channel=1)               # every rank's new blocks are in place
+                ready = torch.cuda.Event()
+                ready.record(side)
+            up.wait_event(ready)
+        trace.mark("exchange: pulls begin", up)
         device = torch.device("cuda", torch.cuda.current_device())
         for h, dst in moves:
             if dst != rank:
                 continue
-            remote = self.handle.get_buffer(h.home, h.shape, torch.float64, offsets[h.hid])
+            remote = self.handle.get_buffer(h.home, h.shape, torch.float64, self.slots[h.hid][1])
             with torch.cuda.stream(up):
                 dev = torch.empty(h.shape, dtype=torch.float64, device=device)
                 dev.copy_(remote, non_blocking=True)
@@ -833,18 +875,28 @@ class SpmdSystem(object):
             self.backend.flush()
             return
         self.stats["flushes"] += 1
-        # A. operands that must travel: one batched exchange.  The operands of every block's FIRST term go
-        #    first, so that a launch over all blocks can start after a fraction of the exchange (see B).
-        moves, seen = [], set()
-        for first_only in (True, False):
-            for h in alive:
-                dots = [it for it in h.lazy.items if it[0] == "dot"]
-                for it in (dots[:1] if first_only else dots[1:]):
-                    for operand in (it[1], it[2]):
-                        key = (operand.hid, it[-1])
-                        if key not in seen and not operand.available_on(it[-1]):
-                            seen.add(key)
-                            moves.append((operand, it[-1]))
+        # A. operands that must travel: one batched exchange.  Every block gets a HEAD term -- the one with most
+        #    operand bytes already on its executing rank (often fully local) -- whose missing operands go first;
+        #    the other terms follow in k order rotated past the head, so that at any moment different ranks pull
+        #    from different owners instead of all hitting the owners of k = 0.
+        moves, seen, heads = [], set(), {}
+        rounds = {}
+        for h in alive:
+            dots = [it for it in h.lazy.items if it[0] == "dot"]
+            if not dots:
+                continue
+            local_bytes = [sum(op.nbytes for op in (it[1], it[2]) if op.available_on(it[-1])) for it in dots]
+            head = max(range(len(dots)), key=lambda t: (local_bytes[t], -t))
+            heads[h.hid] = dots[head]
+            for t, it in enumerate(dots):
+                rounds.setdefault((t - head) % len(dots), []).append(it)
+        for rnd in sorted(rounds):
+            for it in rounds[rnd]:
+                for operand in (it[1], it[2]):
+                    key = (operand.hid, it[-1])
+                    if key not in seen and not operand.available_on(it[-1]):
+                        seen.add(key)
+                        moves.append((operand, it[-1]))
         if self._peer is not None:
             self._peer.pulled = False
         self._move_many(moves)
@@ -862,11 +914,12 @@ class SpmdSystem(object):
             if build is not None and len(mine) > 1 and all(it[0] == "dot" for it in mine):
                 # the whole k-chain of this block as ONE deferred contraction (no per-term dot / add replay)
                 terms = [(it[1].value, it[2].value, it[3], it[4], it[5], it[6]) for it in mine]
-                if overlap and len(terms) >= 3:
-                    head = build(terms[:1], h.shape)
+                if overlap and len(terms) >= 3 and heads.get(h.hid) in mine:
+                    at = mine.index(heads[h.hid])
+                    head = build(terms[at:at + 1], h.shape)
                     if head is not None:
                         partial[h.hid], borrowed[h.hid] = head, False
-                        tails.append((h, head, terms[1:]))
+                        tails.append((h, head, terms[:at] + terms[at + 1:]))
                         continue
                 acc = build(terms, h.shape)
                 if acc is not None:
