@@ -585,7 +585,99 @@ def api_workloads(host, quick):
         "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters) / 1e9}
     del X, y
     torch.cuda.empty_cache()
+    if world >= 8 and not quick:
+        out["large_matmul_65536"] = large_matmul_workload(host, steps=2)
     return out
+
+
+def large_matmul_workload(host, steps=2, n=65536, bs=8192, samples=8):
+    """BASELINE.json configs[4] through the plugin API: float64 65536 x 65536 @ 65536 x 65536 on an 8 x 8 grid of
+    8192 x 8192 blocks (34.4 GB per operand), BlockArray.__matmul__ over SpmdSystem (or CudaSystem at N = 1).
+    Blocks are generated on their owners' devices (seeded per block).  Parity: a 128 x 128 corner of `samples`
+    different C blocks against NumPy on the host, from the matching slices of the operand blocks."""
+    import torch
+    import torch.distributed as dist
+    system = host.system
+    world, rank = getattr(system, "world_size", 1), getattr(system, "rank", 0)
+    spmd = world > 1
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = n // bs
+
+    def block(seed, i, j):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed * 1000 + i * g + j)
+        return torch.randn((bs, bs), dtype=torch.float64, device=dev, generator=gen)
+
+    def operand(seed):
+        ba = host.blockarray((n, n), (bs, bs), "float64")
+        for (i, j) in ba.grid.get_entry_iterator():
+            if spmd:
+                mine = system.owner((i, j), (g, g)) == rank
+                ba.blocks[i, j].oid = system.put_at(block(seed, i, j) if mine else None, (i, j), (g, g),
+                                                    shape=(bs, bs), dtype=np.float64)
+            else:
+                ba.blocks[i, j].oid = block(seed, i, j)
+        return ba
+
+    def sync():
+        system.synchronize()
+        if spmd:
+            dist.barrier()
+            torch.cuda.synchronize()
+    A, B = operand(3), operand(4)
+
+    def product():
+        if spmd:
+            system.evict_copies()
+        c = A @ B
+        system.flush()
+        return c
+    c = product()                       # warm-up (also stages the operands into the peer arenas at N > 1)
+    sync()
+    c = None
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        c = None
+        c = product()
+    end.record()
+    end.synchronize()
+    sync()
+    t = torch.tensor([start.elapsed_time(end) * 1e-3], dtype=torch.float64, device=dev)
+    if spmd:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    seconds = float(t.item()) / steps
+    # parity on sampled corners: the owner of each block cuts the slice, rank 0 receives it
+    def corner(ba, i, j, rows, cols):
+        oid = ba.blocks[i, j].oid
+        if not spmd:
+            return system.get(system.contractions.resolve(oid)[rows, cols])
+        home = oid.home
+        piece = torch.empty((128, bs) if cols == slice(None) else ((bs, 128) if rows == slice(None) else (128, 128)),
+                            dtype=torch.float64, device=dev)
+        if rank == home:
+            piece.copy_(system.backend.settle(oid.value)[rows, cols])
+        dist.broadcast(piece, src=home)
+        return piece.cpu().numpy()
+    errs = []
+    top = slice(0, 128)
+    for s_ in range(samples):
+        i, j = (3 * s_ + 1) % g, (5 * s_ + 2) % g
+        got = corner(c, i, j, top, top)
+        ref = np.zeros((128, 128))
+        for k in range(g):
+            ref += corner(A, i, k, top, slice(None)) @ corner(B, k, j, slice(None), top)
+        errs.append(float(np.linalg.norm(got - ref) / np.linalg.norm(ref)))
+    resident = torch.cuda.max_memory_allocated() / 1e9
+    del A, B, c
+    torch.cuda.empty_cache()
+    flops = 2.0 * n ** 3
+    return {"value": flops / seconds / 1e12, "unit": "TFLOP/s", "ms": seconds * 1e3, "steps": steps,
+            "workload": "blocked matmul float64 65536x65536 @ 65536x65536, 8x8 grid of 8192x8192 blocks (BASELINE.json "
+                        "configs[4]) through BlockArray.__matmul__ on %d GPU(s)" % world,
+            "parity_rel_err_max": max(errs), "parity_samples": samples, "parity_bar": 1e-10,
+            "parity_what": "128x128 corner of %d different C blocks vs NumPy on the host" % samples,
+            "peak_allocated_gb_per_gpu": resident}
 
 
 def run_large(args):
@@ -594,7 +686,7 @@ def run_large(args):
     parity is checked on a sampled 512 x 512 corner of one C block against NumPy on the host."""
     import torch
     import torch.distributed as dist
-    from nums_b200 import _lib, multi_gpu
+    from nums_b200 import _lib, multi_gpu, reference_compat
     from nums_b200.cuda_system import CudaSystem
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -602,6 +694,23 @@ def run_large(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=multi_gpu.nccl_options())
+    if reference_compat.available() and not args.summa_driver:
+        # through the plugin API: the reference's BlockArray.__matmul__ over CudaSystem (N = 1) / SpmdSystem (N > 1)
+        from nums_b200.host import HostLayers
+        host = HostLayers()
+        w = large_matmul_workload(host, steps=args.steps)
+        if rank == 0:
+            emit({"metric": "blocked_matmul_fp64_tflops", "value": w["value"], "unit": "TFLOP/s", "n_gpus": world,
+                  "steps": args.steps, "warmup": 1, "ms_per_step": w["ms"], "higher_is_better": True, "scaling": "strong",
+                  "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                  "config": {"workload": w["workload"], "host_layers": host.description,
+                             "parity_rel_err": w["parity_rel_err_max"]},
+                  "parity_check": {"what": w["parity_what"], "rel_err": w["parity_rel_err_max"], "bar": 1e-10},
+                  "resident_gb_per_gpu": w["peak_allocated_gb_per_gpu"]})
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     comm = multi_gpu.Comm()
     system = CudaSystem(rank=rank, world_size=world)
     system.init()
@@ -804,12 +913,18 @@ def run_gpu(args):
     t_mark0 = sampler.mark()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
+    host_step_ms = []
     for _ in range(args.steps):
+        t_host = time.perf_counter()
         step_resident()
+        host_step_ms.append((time.perf_counter() - t_host) * 1e3)
     end.record()
     end.synchronize()
     sync_all()
     t_mark1 = sampler.mark()
+    if os.environ.get("NUMS_TRACE") == "1":
+        sys.stderr.write("TRACE[rank %d] timed region: device %.1f ms, host enqueue per step: %s\n"
+                         % (rank, start.elapsed_time(end), " ".join("%.1f" % m for m in host_step_ms)))
     launches = LIB.dll.nums_launch_count() - launches0
     elapsed = torch.tensor([start.elapsed_time(end) * 1e-3], dtype=torch.float64, device="cuda")
     if world > 1:
