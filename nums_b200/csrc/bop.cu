@@ -97,6 +97,54 @@ bop_dense_kernel(const typename storage_of<T>::type* __restrict__ a,
   }
 }
 
+// Row / column broadcast kernel: out(r, c) = OP(X(r, c), v) with X and out dense (rows x cols) and the
+// other operand either one value per row (`s * X` with s of shape (n, 1), glms.py:236) or one value per
+// column (`X - mean` with mean of shape (1, d), application.py:510-512).  Same 128-bit streaming accesses
+// as the dense kernel; the small operand goes through the read-only cache (each value is reused `cols` /
+// `rows` times).  cols is a multiple of the vector width, so a vector never straddles two rows.
+enum { kPerRow = 0, kPerCol = 1 };
+template <class OP, typename T, int KIND, bool SMALL_IS_A>
+__global__ void __launch_bounds__(kThreads)
+bop_rowcol_kernel(const typename storage_of<T>::type* __restrict__ x, const void* __restrict__ small, int small_dtype,
+                  int64_t small_stride, typename storage_of<typename OP::Out>::type* __restrict__ out,
+                  uint32_t n, uint32_t cols) {
+  using S = typename storage_of<T>::type;
+  using O = typename OP::Out;
+  using OS = typename storage_of<O>::type;
+  constexpr int VEC = 16 / sizeof(S);
+  constexpr uint32_t kTile = kThreads * kUnroll * VEC;
+  const uint32_t base = blockIdx.x * kTile;
+  if (base + kTile <= n) {
+    const uint32_t v0 = base / VEC + threadIdx.x;
+    Vec<S, VEC> vx[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) vx[u] = load_vec<S, VEC>(x, (int64_t)v0 + (int64_t)u * kThreads);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t e = (v0 + u * kThreads) * VEC;
+      const uint32_t row = e / cols, col = e - row * cols;
+      T per_row = T(0);
+      if constexpr (KIND == kPerRow) per_row = load_as<T>(small, small_dtype, (int64_t)row * small_stride);
+      Vec<OS, VEC> vo;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        T sv = per_row;
+        if constexpr (KIND == kPerCol) sv = load_as<T>(small, small_dtype, (int64_t)(col + j) * small_stride);
+        T xv = from_storage<T>(vx[u].v[j]);
+        vo.v[j] = to_storage<O>(SMALL_IS_A ? OP::apply(sv, xv) : OP::apply(xv, sv));
+      }
+      store_vec<OS, VEC>(out, (int64_t)v0 + (int64_t)u * kThreads, vo);
+    }
+  } else {
+    for (uint32_t i = base + threadIdx.x; i < n; i += kThreads) {
+      const uint32_t row = i / cols, col = i - row * cols;
+      T sv = load_as<T>(small, small_dtype, (int64_t)(KIND == kPerRow ? row : col) * small_stride);
+      T xv = from_storage<T>(x[i]);
+      out[i] = to_storage<O>(SMALL_IS_A ? OP::apply(sv, xv) : OP::apply(xv, sv));
+    }
+  }
+}
+
 // General kernel: any broadcast / stride pattern over <= 8 collapsed axes, operands converted
 // from their storage dtype to the loop dtype on load (e.g. f64 array (+) f32 0-d scalar from
 // BlockArray.from_scalar, blockarray.py:47-58; `s * X`, glms.py:236; `X - mean`,
@@ -154,6 +202,34 @@ int launch_bop(const Layout3& L, const nums_array_t* a, const nums_array_t* b,
     if (b_dense && a_scalar && aligned16(b->data)) {
       bop_dense_kernel<OP, T, kScalarA><<<grid, kThreads, 0, stream>>>(
           nullptr, static_cast<const S*>(b->data), a->data, a->dtype, o, n);
+      NUMS_LAUNCH_OK();
+      return NUMS_OK;
+    }
+  }
+  if constexpr (std::is_floating_point<T>::value)     // (the float loops are the ones on the hot path; keeps build time down)
+  if (out_dense && out_al && L.ndim == 2 && n < (int64_t)0x7fffffff && L.shape[1] % VEC == 0) {
+    // (rows, cols) (+) (rows, 1) / (1, cols): one dense operand, the other constant along one axis
+    const unsigned grid = blocks_for(n, kThreads * kUnroll * VEC);
+    OS* o = static_cast<OS*>(out->data);
+    const uint32_t cols = (uint32_t)L.shape[1];
+    for (int small_op = 1; small_op <= 2; ++small_op) {
+      const int big_op = 3 - small_op;
+      const nums_array_t* big = big_op == 1 ? a : b;
+      const nums_array_t* small = small_op == 1 ? a : b;
+      const bool big_dense = (big_op == 1 ? a_dense : b_dense) && aligned16(big->data);
+      if (!big_dense) continue;
+      const int64_t s0 = L.stride[small_op][0], s1 = L.stride[small_op][1];
+      const bool per_row = s1 == 0 && s0 != 0, per_col = s0 == 0 && s1 != 0;
+      if (!per_row && !per_col) continue;
+      const S* xp = static_cast<const S*>(big->data);
+#define NUMS_ROWCOL(KIND, SMALL_A)                                                                      \
+      bop_rowcol_kernel<OP, T, KIND, SMALL_A><<<grid, kThreads, 0, stream>>>(                             \
+          xp, small->data, small->dtype, (KIND) == kPerRow ? s0 : s1, o, (uint32_t)n, cols)
+      if (per_row && small_op == 1) NUMS_ROWCOL(kPerRow, true);
+      else if (per_row) NUMS_ROWCOL(kPerRow, false);
+      else if (small_op == 1) NUMS_ROWCOL(kPerCol, true);
+      else NUMS_ROWCOL(kPerCol, false);
+#undef NUMS_ROWCOL
       NUMS_LAUNCH_OK();
       return NUMS_OK;
     }

@@ -70,10 +70,22 @@ def block_rng(seed, jump_index):
 # ---------------------------------------------------------------------------------------------
 # plumbing helpers (metadata + allocation only)
 # ---------------------------------------------------------------------------------------------
+_DEVICES = {}
+
+
 def _device():
-    if not torch.cuda.is_available():
-        raise _lib.NumsCudaError("cuda_compute needs a CUDA device; there is no CPU fallback")
-    return torch.device("cuda", torch.cuda.current_device())
+    """torch.device of this process' GPU (one process drives one GPU; cached per current device index --
+    this sits on the per-block dispatch path)."""
+    try:
+        index = torch.cuda.current_device()
+    except Exception:  # noqa: BLE001 -- no driver / no device
+        index = None
+    dev = _DEVICES.get(index)
+    if dev is None:
+        if index is None or not torch.cuda.is_available():
+            raise _lib.NumsCudaError("cuda_compute needs a CUDA device; there is no CPU fallback")
+        dev = _DEVICES[index] = torch.device("cuda", index)
+    return dev
 
 
 class _Transfers(object):
@@ -753,16 +765,25 @@ class ComputeCls(_ComputeImp):
 # helpers (module level: ComputeCls itself must expose nothing but the 28 interface methods,
 # the reference's SerialSystem.init looks every method up in ComputeInterface, systems.py:76-89)
 # ---------------------------------------------------------------------------------------------
+_BOP_PLANS = {}      # (ufunc name, torch dtype a, torch dtype b) -> (op code, loop dtype code, output torch dtype)
+
+
 def elementwise(name, a1, a2):
     """np.<name>(a1, a2) with NumPy type resolution and broadcasting (nums_bop)."""
-    if name not in _lib.BOP_CODE:
-        raise NotImplementedError("binary ufunc %s" % name)
-    loop, out_dt = bop_types(name, _lib.numpy_dtype(a1.dtype), _lib.numpy_dtype(a2.dtype))
-    shape = _broadcast_shape(tuple(a1.shape), tuple(a2.shape))
-    out = _empty(shape, out_dt)
+    key = (name, a1.dtype, a2.dtype)
+    plan = _BOP_PLANS.get(key)
+    if plan is None:
+        if name not in _lib.BOP_CODE:
+            raise NotImplementedError("binary ufunc %s" % name)
+        loop, out_dt = bop_types(name, _lib.numpy_dtype(a1.dtype), _lib.numpy_dtype(a2.dtype))
+        plan = _BOP_PLANS[key] = (_lib.BOP_CODE[name], _lib.dtype_code(loop), _lib.torch_dtype(out_dt))
+    s1, s2 = a1.shape, a2.shape
+    shape = s1 if s1 == s2 else _broadcast_shape(tuple(s1), tuple(s2))
+    out = torch.empty(shape, dtype=plan[2], device=a1.device)
     if out.numel():
-        LIB.check(LIB.dll.nums_bop(_lib.BOP_CODE[name], _lib.dtype_code(loop), describe(a1), describe(a2),
-                                   describe(out), _stream()))
+        rc = LIB.dll.nums_bop(plan[0], plan[1], describe(a1), describe(a2), describe(out), _stream())
+        if rc:
+            LIB.check(rc)
     return out
 
 
@@ -1258,6 +1279,33 @@ def delete_block_fs(filename, grid_entry):
     import os
     os.remove(_block_path(filename, grid_entry))
     return None
+
+
+# ---------------------------------------------------------------------------------------------
+# optional kernels beyond ComputeInterface: offered to the host layers as
+# ``system.lr_grad_hess`` / ``system.newton_step`` (CudaSystem registers EXTRA_KERNELS at init) and used
+# by nums_b200.glms_fused when present.  Same calling convention as the 28 interface methods: blocks in,
+# blocks out, ``syskwargs`` stripped by the system.
+# ---------------------------------------------------------------------------------------------
+def lr_grad_hess_block(X, y, beta):
+    """g | H of one (n_b, d) row block: what glms.forward / gradient / hessian (glms.py:140-143,213-240)
+    compute with ~12 kernel calls and six passes over X, in ONE pass (nums_lr_grad_hess_blocks when the
+    block is dense and d = 4 or 12 mod 16, nums_lr_grad_hess otherwise)."""
+    X, y, beta = upload(X), upload(y), upload(beta)
+    if y.dim() != 1:
+        y = _reshape(y, (y.numel(),))
+    return lr_grad_hess_blocks([X], [y], beta)
+
+
+def newton_step_block(gh, beta):
+    """(beta - inv(H) g, status = {max |g|, info}) from the summed g | H buffer (glms.py:368-370)."""
+    return newton_step(upload(gh), upload(beta))
+
+
+EXTRA_KERNELS = {
+    "lr_grad_hess": lr_grad_hess_block,
+    "newton_step": newton_step_block,
+}
 
 
 def loadtxt_block(fname, dtype, comments, delimiter, converters, skiprows, usecols, unpack, ndmin, encoding,

@@ -79,6 +79,10 @@ class CudaSystem(object):
                 continue
             self.remote_functions[name] = fn
             self.methods[name] = self._make_callable(name)
+        # optional kernels beyond the 28 interface methods (fused logistic-regression step)
+        for name, fn in getattr(self.compute_module, "EXTRA_KERNELS", {}).items():
+            self.remote_functions[name] = fn
+            self.methods[name] = self._make_callable(name)
 
     def shutdown(self):
         # like SerialSystem.shutdown (systems.py:91-92) this leaves the system usable: the reference keeps
@@ -188,8 +192,7 @@ class CudaSystem(object):
 
     # -- dispatch -----------------------------------------------------------------------------------
     def call(self, name, *args, **kwargs):
-        kwargs = dict(kwargs)
-        kwargs.pop("syskwargs", None)
+        kwargs.pop("syskwargs", None)        # (**kwargs is a fresh dict per call)
         q = self.contractions
         if name == "bop" and q.enabled:
             op = args[0] if args else kwargs.get("op")

@@ -295,6 +295,12 @@ def infer_result(name, args, kwargs, meta_of):
         if name in ("update_block_by_index", "update_block_along_axis"):
             shape, dt = meta_of(args[0])
             return blk(shape, dt)
+        if name == "lr_grad_hess":
+            d = int(meta_of(args[2])[0][0])
+            return blk((d + d * d,), np.float64)
+        if name == "newton_step":
+            d = int(meta_of(args[1])[0][0])
+            return ("t", [blk((d,), np.float64), blk((2,), np.float64)])
     except Exception:  # noqa: BLE001 -- anything unusual: let the executing rank describe the result
         return None
     return None

@@ -758,3 +758,78 @@ def test_batched_scatter_kernels(cuda_system, oracle):
     assert_exact(got, oracle.update_block_by_index(di, sf, pairs))
     with pytest.raises(IndexError):
         cuda_system.update_block_by_index(cuda_system.put(di), cuda_system.put(sf), [((3, 0), (0, 0))], syskwargs={})
+
+
+# ----------------------------------------------------------------------------------------------------
+# qr: graded spectra -- every branch of cuda_compute.qr_r_ex (one Cholesky pass, CholeskyQR2, Householder)
+# ----------------------------------------------------------------------------------------------------
+def _graded(m, n, kappa, seed, dtype=np.float64):
+    """m x n matrix with singular values log-spaced from 1 down to 1/kappa."""
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    return ((U * np.logspace(0, -np.log10(kappa), n)) @ V.T).astype(dtype)
+
+
+def _qr_r_checks(cuda_system, X, r_tol, gram_tol):
+    from nums_b200 import cuda_compute as cc
+    before = dict(cc.QR_STATS)
+    R = cuda_system.get(cuda_system.qr(cuda_system.put(X), mode="r", axis=None, syskwargs={}))
+    ran = {k: cc.QR_STATS[k] - before[k] for k in before}
+    X64 = X.astype(np.float64)
+    assert R.shape == (X.shape[1], X.shape[1]) and np.allclose(np.tril(R, -1), 0)
+    # backward stability, independent of row signs: R^T R = X^T X
+    G = X64.T @ X64
+    assert np.linalg.norm(R.astype(np.float64).T @ R.astype(np.float64) - G) / np.linalg.norm(G) <= gram_tol
+    if r_tol is not None:
+        Rw = np.linalg.qr(X64, mode="r")
+        assert rel_fro(_canon(R), _canon(Rw)) <= r_tol, rel_fro(_canon(R), _canon(Rw))
+    return ran
+
+
+@pytest.mark.parametrize("kappa,branch,r_tol", [(1e0, "gram", 1e-10), (2e1, "gram2", 1e-10), (1e2, "gram2", 1e-10),
+                                               (1e5, "gram2", 1e-10), (1e9, "householder", None),
+                                               (1e13, "householder", None)])
+def test_qr_graded_spectrum_branches(cuda_system, kappa, branch, r_tol):
+    """Tall float64 blocks of growing condition number: the 1e-10 sign-canonical bar on R must hold wherever
+    it is meaningful (two backward-stable factorizations agree to ~kappa * eps only), backward stability must
+    hold everywhere, and the branch the condition bound selects is the expected one."""
+    X = _graded(40_000, 64, kappa, seed=int(np.log10(kappa)) + 7)
+    ran = _qr_r_checks(cuda_system, X, r_tol, gram_tol=1e-13)
+    assert ran[branch] == 1 and sum(ran.values()) == 1, ran
+    Q, R = cuda_system.qr(cuda_system.put(X), mode="reduced", axis=None, syskwargs={})
+    Q, R = cuda_system.get(Q), cuda_system.get(R)
+    assert rel_fro(Q @ R, X) <= 1e-12
+    if kappa <= 1e5:
+        assert np.linalg.norm(Q.T @ Q - np.eye(64)) <= 1e-10
+
+
+def test_qr_rank_deficient_and_float32(cuda_system):
+    rng = np.random.default_rng(77)
+    X = rng.standard_normal((30_000, 32))
+    X[:, 7] = X[:, 3]                        # exactly rank deficient: the Gram matrix is not positive definite
+    X[:, 20] = 0.5 * X[:, 1] - 2.0 * X[:, 2]
+    ran = _qr_r_checks(cuda_system, X, None, gram_tol=1e-13)
+    assert ran["householder"] == 1 and ran["gram"] == 0 and ran["gram2"] == 0, ran
+    X32 = rng.standard_normal((50_000, 48)).astype(np.float32)     # float32 tall block: Householder kernel
+    ran = _qr_r_checks(cuda_system, X32, 2e-5, gram_tol=2e-6)
+    assert ran["householder"] == 1, ran
+    Xz = np.zeros((4096, 16))
+    R = cuda_system.get(cuda_system.qr(cuda_system.put(Xz), mode="r", axis=None, syskwargs={}))
+    assert np.array_equal(R, np.zeros((16, 16)))
+
+
+def test_bop_row_and_column_broadcast_large(cuda_system, oracle):
+    """(n, d) (+) (n, 1) / (1, d) / (d,) at sizes that use the 128-bit row/column broadcast kernel, both operand
+    orders, float64 and float32, comparison results, plus shapes that must fall back to the strided kernel."""
+    rng = np.random.default_rng(9)
+    for n, d in ((60_000, 28), (4_099, 6), (1_000, 7)):          # d = 7: odd width -> generic strided kernel
+        X = rng.standard_normal((n, d))
+        col, row, vec = rng.standard_normal((n, 1)), rng.standard_normal((1, d)), rng.standard_normal(d)
+        for op in ("add", "sub", "mul", "truediv", "lt", "maximum"):
+            for a, b in ((col, X), (X, col), (X, row), (row, X), (X, vec), (vec, X)):
+                _bop(cuda_system, oracle, op, a, b)
+        _bop(cuda_system, oracle, "mul", col.astype(np.float32), X)          # f32 column, f64 loop
+        X32 = X.astype(np.float32)
+        _bop(cuda_system, oracle, "mul", col.astype(np.float32), X32)
+        _bop(cuda_system, oracle, "sub", X32, row.astype(np.float32))

@@ -192,3 +192,70 @@ def test_reductions_and_argops(nps_cuda):
     v = rng.standard_normal(1000)
     bv = nps.array(v).reshape(block_shape=(128,))
     assert int(nps.argmax(bv).get()) == int(np.argmax(v)) and int(nps.argmin(bv).get()) == int(np.argmin(v))
+
+
+def test_fused_newton_through_glms(apps):
+    """nums_b200.glms_fused: the optional lr_grad_hess / newton_step kernels behind glms.newton and
+    LogisticRegression.fit, against the reference's own newton on numpy_compute."""
+    from nums.models import glms
+    from nums.models.glms import LogisticRegression
+    from nums_b200 import glms_fused
+    from nums_b200._lib import LIB
+    cuda_app, serial_app = apps
+    rng = np.random.default_rng(16)
+    n, d = 64_000, 28
+    X = rng.standard_normal((n, d))
+    theta = rng.standard_normal(d) / np.sqrt(d)
+    y = (rng.random(n) < 1.0 / (1.0 + np.exp(-X @ theta))).astype(np.float64)
+    model = LogisticRegression(solver="newton", penalty="none")
+    model._app = serial_app
+    want = glms.newton(serial_app, model, serial_app.zeros((d,), (d,), dtype=np.float64), serial_app.array(X, (8_000, d)),
+                       serial_app.array(y, (8_000,)), serial_app.scalar(1e-8), 10).get()
+    model._app = cuda_app
+    xb, yb = cuda_app.array(X, (8_000, d)), cuda_app.array(y, (8_000,))
+    launches = LIB.dll.nums_launch_count()
+    got = glms_fused.newton(cuda_app, model, cuda_app.zeros((d,), (d,), dtype=np.float64), xb, yb,
+                            cuda_app.scalar(1e-8), 10).get()
+    fused_launches = LIB.dll.nums_launch_count() - launches
+    assert rel_fro(got, want) <= 1e-10
+    launches = LIB.dll.nums_launch_count()
+    unfused = glms.newton(cuda_app, model, cuda_app.zeros((d,), (d,), dtype=np.float64), xb, yb,
+                          cuda_app.scalar(1e-8), 10).get()
+    assert rel_fro(unfused, want) <= 1e-10
+    assert fused_launches * 5 < LIB.dll.nums_launch_count() - launches      # ~10 launches / iteration instead of ~130
+    # d = 7 is not served by the fused kernels: the same entry point falls back to the reference's newton
+    X7 = X[:, :7].copy()
+    b7 = glms_fused.newton(cuda_app, model, cuda_app.zeros((7,), (7,), dtype=np.float64), cuda_app.array(X7, (8_000, 7)),
+                           yb, cuda_app.scalar(1e-8), 5).get()
+    model._app = serial_app
+    w7 = glms.newton(serial_app, model, serial_app.zeros((7,), (7,), dtype=np.float64), serial_app.array(X7, (8_000, 7)),
+                     serial_app.array(y, (8_000,)), serial_app.scalar(1e-8), 5).get()
+    assert rel_fro(b7, w7) <= 1e-10
+
+
+def test_fit_and_predict_with_repaired_intercept(nps_cuda):
+    """LogisticRegression.fit through the installed fused newton, and the intercept repair of INTEGRATION.md
+    section 3: after ``fit_with_intercept`` the model's ``predict`` works (it raises on the unmodified fork,
+    SURVEY.md section 0.3)."""
+    nps, app = nps_cuda
+    from nums.models import glms
+    from nums_b200 import glms_fused
+    rng = np.random.default_rng(17)
+    n, d = 20_000, 12
+    X = rng.standard_normal((n, d))
+    theta, bias = rng.standard_normal(d), 0.7
+    y = (rng.random(n) < 1.0 / (1.0 + np.exp(-(X @ theta + bias)))).astype(np.float64)
+    glms_fused.install()
+    try:
+        assert glms.newton is glms_fused.newton
+        xb, yb = app.array(X, (5_000, d)), app.array(y, (5_000,))
+        model = glms.LogisticRegression(solver="newton", penalty="none", tol=1e-8, max_iter=10)
+        model.fit(xb, yb)                                 # the fork's fit: no intercept column, beta split anyway
+        model = glms.LogisticRegression(solver="newton", penalty="none", tol=1e-8, max_iter=10)
+        glms_fused.fit_with_intercept(model, xb, yb)
+        beta, beta0 = model._beta.get(), float(model._beta0.get())
+        assert beta.shape == (d,) and abs(beta0 - bias) < 0.1 and np.linalg.norm(beta - theta) < 0.2 * np.linalg.norm(theta)
+        pred = model.predict(xb).get()
+        assert pred.shape == (n,) and np.mean(pred == y) > 0.8
+    finally:
+        glms_fused.uninstall()
