@@ -117,6 +117,12 @@ uint64_t nums_launch_count(void);
 int nums_bop(int op, int loop_dtype, const nums_array_t* a, const nums_array_t* b,
              const nums_array_t* out, void* stream);
 
+/* nums_bop for operands that are dense over the output's iteration space or single values (a_n / b_n:
+ * n = dense, 1 = broadcast scalar): raw pointers instead of array descriptors, for the per-block
+ * dispatch path of BlockArray's elementwise operators (base.py:167-246 -> numpy_compute.py:233-238). */
+int nums_bop_flat(int op, int loop_dtype, const void* a, int a_dtype, int64_t a_n, const void* b,
+                  int b_dtype, int64_t b_n, void* out, int out_dtype, int64_t n, void* stream);
+
 /* out = ufunc(a) (numpy_compute.py:184-186).  NUMS_UOP_COPY is a dtype-converting strided
  * copy: astype (:206-208), the slice copies of create_block/update_block (:119-169), and
  * materialisation of transposed views (:213-214, :222-229). */

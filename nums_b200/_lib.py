@@ -150,6 +150,7 @@ class _Lib(object):
             "nums_sm_count": ([], c.c_int),
             "nums_launch_count": ([], c.c_uint64),
             "nums_bop": ([I, I, A, A, A, P], I),
+            "nums_bop_flat": ([I, I, P, I, L, P, I, L, P, I, L, P], I),
             "nums_uop": ([I, I, A, A, P], I),
             "nums_sum_reduce": ([I, c.POINTER(P), I, L, P, P], I),
             "nums_fill": ([A, D, P], I),
@@ -180,7 +181,7 @@ class _Lib(object):
             fn.restype = restype
 
     EXPORTS = ("nums_abi_version nums_last_error nums_last_workspace_request nums_sm_count nums_launch_count nums_bop "
-               "nums_uop nums_sum_reduce nums_fill nums_arange nums_eye nums_reduce nums_arg_op "
+               "nums_bop_flat nums_uop nums_sum_reduce nums_fill nums_arange nums_eye nums_reduce nums_arg_op "
                "nums_allclose nums_nonzero_count nums_nonzero_fill nums_gemm nums_gemm_grouped nums_qr nums_inv "
                "nums_cholesky nums_gram_factor nums_svd nums_lr_grad_hess nums_lr_grad_hess_blocks nums_newton_step nums_scatter_axis nums_csv_index "
                "nums_csv_parse").split()

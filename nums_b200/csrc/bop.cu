@@ -363,3 +363,26 @@ extern "C" int nums_bop(int op, int loop_dtype, const nums_array_t* a, const num
 #undef INB
   NUMS_FAIL(NUMS_ERR_INVALID, "bop: unknown op id %d", op);
 }
+
+// Same as nums_bop for the two shapes that dominate the per-block dispatch path -- both operands dense over
+// the output's iteration space, or one of them a single value -- without the three array descriptors: the
+// host hands over raw pointers and element counts (a_n / b_n: n = dense, 1 = broadcast scalar).
+extern "C" int nums_bop_flat(int op, int loop_dtype, const void* a, int a_dtype, int64_t a_n, const void* b,
+                             int b_dtype, int64_t b_n, void* out, int out_dtype, int64_t n, void* stream) {
+  using namespace nums;
+  NUMS_REQUIRE((a_n == n || a_n == 1) && (b_n == n || b_n == 1) && n >= 0,
+               "bop_flat: operands must be dense over the output or single values");
+  nums_array_t arr[3];
+  const void* ptr[3] = {a, b, out};
+  const int dt[3] = {a_dtype, b_dtype, out_dtype};
+  const int64_t cnt[3] = {a_n, b_n, n};
+  for (int i = 0; i < 3; ++i) {
+    arr[i].data = const_cast<void*>(ptr[i]);
+    arr[i].dtype = dt[i];
+    arr[i].ndim = 1;
+    arr[i].shape[0] = cnt[i];
+    arr[i].stride[0] = (cnt[i] == n && n != 1) ? 1 : 0;
+  }
+  if (n == 1) arr[2].stride[0] = 1;
+  return nums_bop(op, loop_dtype, &arr[0], &arr[1], &arr[2], stream);
+}

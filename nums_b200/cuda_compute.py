@@ -776,12 +776,20 @@ def elementwise(name, a1, a2):
         if name not in _lib.BOP_CODE:
             raise NotImplementedError("binary ufunc %s" % name)
         loop, out_dt = bop_types(name, _lib.numpy_dtype(a1.dtype), _lib.numpy_dtype(a2.dtype))
-        plan = _BOP_PLANS[key] = (_lib.BOP_CODE[name], _lib.dtype_code(loop), _lib.torch_dtype(out_dt))
+        plan = _BOP_PLANS[key] = (_lib.BOP_CODE[name], _lib.dtype_code(loop), _lib.torch_dtype(out_dt),
+                                  _lib.dtype_code(a1.dtype), _lib.dtype_code(a2.dtype), _lib.dtype_code(out_dt))
     s1, s2 = a1.shape, a2.shape
     shape = s1 if s1 == s2 else _broadcast_shape(tuple(s1), tuple(s2))
     out = torch.empty(shape, dtype=plan[2], device=a1.device)
-    if out.numel():
-        rc = LIB.dll.nums_bop(plan[0], plan[1], describe(a1), describe(a2), describe(out), _stream())
+    n = out.numel()
+    if n:
+        n1, n2 = a1.numel(), a2.numel()
+        if (n1 == n or n1 == 1) and (n2 == n or n2 == 1) and a1.is_contiguous() and a2.is_contiguous():
+            # dense over the output (broadcasting stretched nothing) or a single value: no descriptors needed
+            rc = LIB.dll.nums_bop_flat(plan[0], plan[1], a1.data_ptr(), plan[3], n1, a2.data_ptr(), plan[4], n2,
+                                       out.data_ptr(), plan[5], n, _stream())
+        else:
+            rc = LIB.dll.nums_bop(plan[0], plan[1], describe(a1), describe(a2), describe(out), _stream())
         if rc:
             LIB.check(rc)
     return out

@@ -93,6 +93,9 @@ class ContractionQueue(object):
         self.flushes = 0
         self.enabled = True
         self.group_policy = "even"       # how a flush is cut into launches, see plan_launch_groups
+        self.last_flush = None           # {"contractions", "tile_terms", "redundant_tile_terms"} of the latest flush
+        self.redundant_tile_terms = 0
+        self._warned = False
         self.materialized_seen = False   # deferred handles exist somewhere: keep resolving arguments
 
     # -- building -------------------------------------------------------------------------------
@@ -192,6 +195,7 @@ class ContractionQueue(object):
         if not alive:
             return
         self.flushes += 1
+        self._audit(alive)
         by_flags = {}
         for d in alive:
             by_flags.setdefault(d.flags, []).append(d)
@@ -199,6 +203,48 @@ class ContractionQueue(object):
             launches = self._launch_groups(group)
             for chunk, upto in launches:
                 self._launch(ta, tb, chunk, upto, len(launches) > 1)
+
+    def _audit(self, alive):
+        """Tile accounting of a flush, and the dangling-chain check.
+
+        ``x += dot`` builds a new contraction from the previous partial chain; the partial chain normally dies
+        at once (CPython reference counting).  If something -- typically a loop variable of the caller --
+        still references it when the flush happens, it is materialised on its own: a whole extra block of GEMM
+        work whose result nobody reads (this cost 3.3 ms per product once).  A live
+        contraction whose term list is a proper prefix of another live one is exactly that case: it is counted
+        in ``last_flush["redundant_tiles"]``, reported once with a warning, and raises under
+        ``NUMS_DEFERRED_STRICT=1`` (set by the tests)."""
+        tiles = redundant = 0
+        by_first = {}
+        for d in alive:
+            m, n = d.shape
+            tiles += (-(-m // 128)) * (-(-n // 128)) * max(len(d.terms), 1)
+            if d.terms:
+                by_first.setdefault(id(d.terms[0]), []).append(d)
+        dangling = []
+        for group in by_first.values():
+            if len(group) < 2:
+                continue
+            group.sort(key=lambda d: len(d.terms))
+            keys = [tuple(map(id, d.terms)) for d in group]
+            for i, d in enumerate(group):
+                if any(len(keys[j]) > len(keys[i]) and keys[j][:len(keys[i])] == keys[i] for j in range(i + 1, len(group))):
+                    m, n = d.shape
+                    redundant += (-(-m // 128)) * (-(-n // 128)) * len(d.terms)
+                    dangling.append(d)
+        self.last_flush = {"contractions": len(alive), "tile_terms": tiles, "redundant_tile_terms": redundant}
+        self.redundant_tile_terms += redundant
+        if dangling:
+            import os
+            import warnings
+            msg = ("%d partial dot/add chain(s) were still referenced at flush time and are materialised separately "
+                   "(%d of %d tile-terms of this flush are wasted): drop the intermediate handles (e.g. loop "
+                   "variables) before the flush" % (len(dangling), redundant, tiles))
+            if os.environ.get("NUMS_DEFERRED_STRICT") == "1":
+                raise AssertionError(msg)
+            if not self._warned:
+                self._warned = True
+                warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
     @staticmethod
     def _need(d):

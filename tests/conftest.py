@@ -8,6 +8,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# a flush that materialises a dangling partial dot/add chain is an error in the tests (nums_b200/deferred.py)
+os.environ.setdefault("NUMS_DEFERRED_STRICT", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     # the tests exercise the built artefact: (re)build libnumscuda.so if it is missing (nvcc needed)

@@ -833,3 +833,39 @@ def test_bop_row_and_column_broadcast_large(cuda_system, oracle):
         X32 = X.astype(np.float32)
         _bop(cuda_system, oracle, "mul", col.astype(np.float32), X32)
         _bop(cuda_system, oracle, "sub", X32, row.astype(np.float32))
+
+
+def test_flush_tile_accounting_and_dangling_chain(cuda_system, monkeypatch):
+    """One grouped launch per flush with exactly the expected tile count; a partial k-chain that is still
+    referenced at flush time is detected (deferred.py: ContractionQueue._audit)."""
+    from nums_b200 import blocks
+    rng = np.random.default_rng(5)
+    A, B = rng.standard_normal((512, 512)), rng.standard_normal((512, 512))
+    app = blocks.ArrayApp(cuda_system)
+    a, b = app.array(A, (128, 128)), app.array(B, (128, 128))
+    q = cuda_system.contractions
+    c = a @ b
+    cuda_system.flush()
+    assert q.last_flush == {"contractions": 16, "tile_terms": 16 * 4, "redundant_tile_terms": 0}
+    assert rel_fro(c.get(), A @ B) <= GEMM_TOL
+    # the same chain built by hand, keeping the partial sums alive
+    shape, sk = (128, 128), {"grid_entry": (0, 0), "grid_shape": (4, 4)}
+    keep, acc = [], None
+    for k in range(4):
+        dot = cuda_system.bop("tensordot", a.blocks[0, k].oid, b.blocks[k, 0].oid, shape, shape, False, False, axes=1, syskwargs=sk)
+        acc = dot if acc is None else cuda_system.bop("add", acc, dot, shape, shape, False, False, axes=None, syskwargs=sk)
+        keep.append(acc)
+    with pytest.raises(AssertionError, match="partial dot/add chain"):
+        cuda_system.flush()
+    keep = acc = dot = None
+    monkeypatch.setenv("NUMS_DEFERRED_STRICT", "0")
+    q._warned = False
+    keep, acc = [], None
+    for k in range(4):
+        dot = cuda_system.bop("tensordot", a.blocks[0, k].oid, b.blocks[k, 0].oid, shape, shape, False, False, axes=1, syskwargs=sk)
+        acc = dot if acc is None else cuda_system.bop("add", acc, dot, shape, shape, False, False, axes=None, syskwargs=sk)
+        keep.append(acc)
+    with pytest.warns(RuntimeWarning, match="partial dot/add chain"):
+        cuda_system.flush()
+    assert q.last_flush["redundant_tile_terms"] == 1 + 2 + 3
+    assert rel_fro(cuda_system.get(acc), (A @ B)[:128, :128]) <= GEMM_TOL
