@@ -13,6 +13,7 @@
 // inv / cholesky: single-CTA in-place elimination in shared memory (global scratch beyond
 // ~160 x 160): the matrices on the path are the 28 x 28 LR Hessian and the 128 x 128 TSQR R,
 // so this is latency, not throughput.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace nums {
@@ -159,6 +160,219 @@ int launch_tsqr_auto(const T* A, int64_t lda, int64_t m, int n, int64_t rows_per
   NUMS_FAIL(NUMS_ERR_UNSUPPORTED, "qr: %d columns do not fit the shared-memory TSQR leaf", n);
 }
 
+// =====================================================================================
+// streaming Householder R, blocked: WY panels + FP64 tensor-pipe trailing updates (n <= 128)
+// =====================================================================================
+// Same factorization as tsqr_stream_kernel -- the running triangle R stays in shared memory and every
+// 128-row chunk C is annihilated against it; reflector j couples only row j of R with the chunk -- but the
+// reflectors are generated 8 at a time (one warp, the 128 x 8 panel held in registers, no CTA barrier inside a
+// panel) and applied to everything right of the panel as one compact-WY block reflector
+//     Q^T = H_7 ... H_0 = I - V T^T V^T,   V = [I_8 ; Vc]   (rows j0..j0+7 of R; the chunk rows)
+//     W = R[J, K] + Vc^T C[:, K];   Y = -T^T W;   R[J, K] += Y;   C[:, K] += Vc Y
+// whose two products run on the FP64 tensor pipe (mma.sync m8n8k4 -> DMMA) straight out of shared memory.
+// T follows LAPACK dlarft (forward, columnwise) with V^T V = I + Vc^T Vc.  The unblocked kernel spends its time
+// in 128 CTA-wide barriers and ~16 dependent warp reductions per column; here a chunk costs 16 panel
+// factorizations (8 short steps each, one warp) plus 2 m n^2 flops of DMMA work.  Input may be float32 or
+// float64; the arithmetic is float64 either way.  Columns are padded to a multiple of 8 with zeros (a zero
+// column yields tau = 0, i.e. H = I).
+constexpr int kWyThreads = 256;
+constexpr int kWyChunk = 128;
+constexpr int kWyVPitch = 12;   // 12 = 12 (mod 16): 4 x 4 fragment reads of Vc hit 16 distinct 8-byte banks
+
+__device__ __forceinline__ void qr_dmma884(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+__host__ __device__ inline int wy_roff(int i, int np) { return i * np - (i * (i - 1)) / 2; }   // packed upper triangle
+inline size_t wy_smem_bytes(int np) {
+  const size_t tri = ((size_t)np * (np + 1) / 2 + 1) & ~(size_t)1;
+  const size_t pc = np + 4;
+  return (tri + (size_t)kWyChunk * pc + (size_t)kWyChunk * kWyVPitch + 2 * 8 * pc + 64) * sizeof(double);
+}
+
+template <typename TIN>
+__global__ void __launch_bounds__(kWyThreads, 1)
+tsqr_wy_kernel(const TIN* __restrict__ A, int64_t lda, int64_t m, int n, int np, int64_t rows_per_cta,
+               TIN* __restrict__ Rout, int64_t r_rows, int64_t ldr) {
+  extern __shared__ __align__(16) unsigned char wy_smem[];
+  const int pc = np + 4;                                   // = 4 or 12 (mod 16): conflict-free 4 x 4 fragment reads
+  const int tri = (np * (np + 1) / 2 + 1) & ~1;
+  double* Rp = reinterpret_cast<double*>(wy_smem);         // packed upper triangle of the np x np factor
+  double* C = Rp + tri;                                    // chunk, kWyChunk x np
+  double* V = C + kWyChunk * pc;                           // Vc of the current panel, kWyChunk x 8
+  double* W = V + kWyChunk * kWyVPitch;                    // 8 x np
+  double* Y = W + 8 * pc;                                  // 8 x np
+  double* Tm = Y + 8 * pc;                                 // 8 x 8
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < tri; i += kWyThreads) Rp[i] = 0.0;
+
+  const int64_t row_lo = (int64_t)blockIdx.x * rows_per_cta;
+  int64_t row_hi = row_lo + rows_per_cta;
+  if (row_hi > m) row_hi = m;
+
+  for (int64_t base = row_lo; base < row_hi; base += kWyChunk) {
+    __syncthreads();
+    for (int i = warp; i < kWyChunk; i += kWyThreads / 32) {      // one row per warp: coalesced
+      const int64_t gr = base + i;
+      const bool live = gr < row_hi;
+      for (int c = lane; c < np; c += 32)
+        C[i * pc + c] = (live && c < n) ? (double)A[gr * lda + c] : 0.0;
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < np; j0 += 8) {
+      if (warp == 0) {
+        // ---- panel factorization: rows lane, lane+32, lane+64, lane+96 of the 128 x 8 panel in registers
+        double x[4][8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[r][k] = C[(lane + 32 * r) * pc + j0 + k];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          double* Rrow = Rp + wy_roff(j0 + t, np);           // Rrow[k - t] = R[j0 + t][j0 + k]
+          double sigma = 0.0;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) sigma += x[r][t] * x[r][t];
+          sigma = warp_sum(sigma);
+          const double alpha = Rrow[0];
+          double tau = 0.0, beta = alpha, scale = 0.0;
+          if (sigma != 0.0) {                                 // LAPACK dlarfg
+            const double nrm = sqrt(alpha * alpha + sigma);
+            beta = alpha >= 0.0 ? -nrm : nrm;
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+          }
+          double v[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) v[r] = x[r][t] * scale;
+          __syncwarp();
+#pragma unroll
+          for (int k = t + 1; k < 8; ++k) {                   // H_t on the rest of the panel
+            double w = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) w += v[r] * x[r][k];
+            w = warp_sum(w);
+            const double tw = tau * (w + Rrow[k - t]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) x[r][k] -= tw * v[r];
+            __syncwarp();
+            if (lane == 0) Rrow[k - t] -= tw;
+          }
+          double g[8];                                        // (Vc^T Vc)[s][t], s < t
+#pragma unroll
+          for (int q = 0; q < 8; ++q) g[q] = 0.0;
+#pragma unroll
+          for (int q = 0; q < t; ++q) {
+            double d = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) d += x[r][q] * v[r];
+            g[q] = warp_sum(d);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) x[r][t] = v[r];
+          // T(0:t-1, t) = -tau T(0:t-1, 0:t-1) g ; T(t, t) = tau          (dlarft, forward columnwise)
+          if (lane < t) {
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (u >= lane && u < t) acc += Tm[lane * 8 + u] * g[u];
+            Tm[lane * 8 + t] = -tau * acc;
+          }
+          if (lane == 0) {
+            Tm[t * 8 + t] = tau;
+            Rrow[0] = beta;
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) V[(lane + 32 * r) * kWyVPitch + k] = x[r][k];
+      }
+      __syncthreads();
+      const int k_first = j0 + 8;
+      const int ntiles = (np - k_first) >> 3;
+      if (ntiles > 0) {
+        const int fr = lane & 3, fc = lane >> 2;              // fragment coordinates of this lane
+        // ---- W = R[J, K] + Vc^T C[:, K]: one 8-column tile per warp at a time, 128-deep contraction
+        for (int tile = warp; tile < ntiles; tile += kWyThreads / 32) {
+          const int k0 = k_first + 8 * tile;
+          double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+#pragma unroll 4
+          for (int r0 = 0; r0 < kWyChunk; r0 += 8) {
+            qr_dmma884(acc0, V[(r0 + fr) * kWyVPitch + fc], C[(r0 + fr) * pc + k0 + fc]);
+            qr_dmma884(acc1, V[(r0 + 4 + fr) * kWyVPitch + fc], C[(r0 + 4 + fr) * pc + k0 + fc]);
+          }
+          const int t = fc, kk = k0 + 2 * fr;                 // accumulator holds W[t][kk], W[t][kk + 1]
+          const double* Rrow = Rp + wy_roff(j0 + t, np) - (j0 + t);
+          W[t * pc + kk] = acc0[0] + acc1[0] + Rrow[kk];
+          W[t * pc + kk + 1] = acc0[1] + acc1[1] + Rrow[kk + 1];
+        }
+        __syncthreads();
+        // ---- Y = -T^T W ; R[J, K] += Y
+        const int ncols = np - k_first;
+        for (int e = threadIdx.x; e < 8 * ncols; e += kWyThreads) {
+          const int t = e / ncols, k = k_first + (e - t * ncols);
+          double y = 0.0;
+          for (int q = 0; q <= t; ++q) y += Tm[q * 8 + t] * W[q * pc + k];
+          Y[t * pc + k] = -y;
+          Rp[wy_roff(j0 + t, np) + k - (j0 + t)] -= y;
+        }
+        __syncthreads();
+        // ---- C[:, K] += Vc Y: 16 row tiles, two per warp; the two A fragments of a row tile are loaded once
+        for (int mt = warp; mt < kWyChunk / 8; mt += kWyThreads / 32) {
+          const int m0 = 8 * mt;
+          const double a0 = V[(m0 + fc) * kWyVPitch + fr], a1 = V[(m0 + fc) * kWyVPitch + 4 + fr];
+          for (int tile = 0; tile < ntiles; ++tile) {
+            const int k0 = k_first + 8 * tile;
+            double2* cp = reinterpret_cast<double2*>(&C[(m0 + fc) * pc + k0 + 2 * fr]);
+            double2 cv = *cp;
+            double acc[2] = {cv.x, cv.y};
+            qr_dmma884(acc, a0, Y[fr * pc + k0 + fc]);
+            qr_dmma884(acc, a1, Y[(4 + fr) * pc + k0 + fc]);
+            cv.x = acc[0];
+            cv.y = acc[1];
+            *cp = cv;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  TIN* out = Rout + (size_t)blockIdx.x * r_rows * ldr;
+  for (int i = warp; i < (int)r_rows; i += kWyThreads / 32) {
+    const double* Rrow = Rp + wy_roff(i, np) - i;
+    for (int c = lane; c < n; c += 32) out[(size_t)i * ldr + c] = (c >= i) ? (TIN)Rrow[c] : TIN(0);
+  }
+}
+
+template <typename T>
+int launch_tsqr_wy(const T* A, int64_t lda, int64_t m, int n, int64_t rows_per_cta, int ctas, T* Rout, int64_t r_rows,
+                   int64_t ldr, cudaStream_t s) {
+  const int np = (n + 7) & ~7;
+  const size_t smem = wy_smem_bytes(np);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(tsqr_wy_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tsqr_wy_kernel<T><<<ctas, kWyThreads, smem, s>>>(A, lda, m, n, np, rows_per_cta, Rout, r_rows, ldr);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
+bool qr_use_wy(int n) {
+  static const bool disabled = [] { const char* e = getenv("NUMS_QR_UNBLOCKED"); return e && e[0] == '1'; }();
+  return !disabled && n <= 128;
+}
+
+template <typename T>
+int launch_leaf(const T* A, int64_t lda, int64_t m, int n, int64_t rows_per_cta, int ctas, T* Rout, int64_t r_rows,
+                int64_t ldr, cudaStream_t s) {
+  if (qr_use_wy(n)) return launch_tsqr_wy<T>(A, lda, m, n, rows_per_cta, ctas, Rout, r_rows, ldr, s);
+  return launch_tsqr_auto<T>(A, lda, m, n, rows_per_cta, ctas, Rout, r_rows, ldr, s);
+}
+
 template <typename T>
 int run_qr_r(int64_t m, int64_t n64, const T* A, int64_t lda, T* R, int64_t ldr, void* ws, size_t ws_bytes,
              cudaStream_t s) {
@@ -172,7 +386,7 @@ int run_qr_r(int64_t m, int64_t n64, const T* A, int64_t lda, T* R, int64_t ldr,
   if (ctas < 1) ctas = 1;
   int64_t rows_per_cta = ceil_div(m, ctas);
   ctas = ceil_div(m, rows_per_cta);
-  if (ctas == 1) return launch_tsqr_auto<T>(A, lda, m, n, rows_per_cta, 1, R, k, ldr, s);
+  if (ctas == 1) return launch_leaf<T>(A, lda, m, n, rows_per_cta, 1, R, k, ldr, s);
   // ping-pong buffers of stacked n x n triangles
   const size_t level0 = (size_t)ctas * n * n * sizeof(T);
   const size_t level1 = (size_t)ceil_div(ctas, 4) * n * n * sizeof(T);
@@ -180,15 +394,15 @@ int run_qr_r(int64_t m, int64_t n64, const T* A, int64_t lda, T* R, int64_t ldr,
   NUMS_NEED_WS(off1 + level1, ws_bytes);
   T* buf0 = static_cast<T*>(ws);
   T* buf1 = reinterpret_cast<T*>(static_cast<char*>(ws) + off1);
-  if (int rc = launch_tsqr_auto<T>(A, lda, m, n, rows_per_cta, (int)ctas, buf0, n, n, s)) return rc;
+  if (int rc = launch_leaf<T>(A, lda, m, n, rows_per_cta, (int)ctas, buf0, n, n, s)) return rc;
   T* src = buf0;
   T* dst = buf1;
   int64_t count = ctas;
   while (count > 1) {
     const int64_t next = ceil_div(count, 4);
     const int64_t rows = count * n;
-    if (next == 1) return launch_tsqr_auto<T>(src, n, rows, n, rows, 1, R, k, ldr, s);
-    if (int rc = launch_tsqr_auto<T>(src, n, rows, n, 4 * (int64_t)n, (int)next, dst, n, n, s)) return rc;
+    if (next == 1) return launch_leaf<T>(src, n, rows, n, rows, 1, R, k, ldr, s);
+    if (int rc = launch_leaf<T>(src, n, rows, n, 4 * (int64_t)n, (int)next, dst, n, n, s)) return rc;
     T* tmp = src;
     src = dst;
     dst = tmp;

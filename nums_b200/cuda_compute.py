@@ -869,6 +869,8 @@ QR_GRAM_MAX_COLS = 256
 QR_GRAM_ACCEPT_KAPPA = 30.0   # one Cholesky pass: error ~ kappa^2 eps  (< 1e-12)
 QR_GRAM_REFINE_KAPPA = 1.0e6  # two passes (CholeskyQR2) are as good as Householder below ~1e7
 QR_STATS = {"gram": 0, "gram2": 0, "householder": 0}
+# NUMS_QR_GRAM=0 sends every block through the Householder kernel (measurements, paranoia)
+QR_GRAM_ENABLED = __import__("os").environ.get("NUMS_QR_GRAM", "1") != "0"
 
 
 def _householder_r(arr):
@@ -962,7 +964,7 @@ def qr_r_ex(arr):
     if not arr.is_contiguous():
         arr = _materialize(arr)
     m, n = arr.shape
-    gram_ok = (arr.dtype == torch.float64 and n % 2 == 0 and 2 <= n <= QR_GRAM_MAX_COLS
+    gram_ok = (QR_GRAM_ENABLED and arr.dtype == torch.float64 and n % 2 == 0 and 2 <= n <= QR_GRAM_MAX_COLS
                and m >= QR_GRAM_MIN_ASPECT * n and m >= 1024 and arr.data_ptr() % 16 == 0)
     if not gram_ok:
         return _householder_r(arr), None
