@@ -215,77 +215,103 @@ tsqr_wy_kernel(const TIN* __restrict__ A, int64_t lda, int64_t m, int n, int np,
 
   for (int64_t base = row_lo; base < row_hi; base += kWyChunk) {
     __syncthreads();
-    for (int i = warp; i < kWyChunk; i += kWyThreads / 32) {      // one row per warp: coalesced
-      const int64_t gr = base + i;
-      const bool live = gr < row_hi;
-      for (int c = lane; c < np; c += 32)
-        C[i * pc + c] = (live && c < n) ? (double)A[gr * lda + c] : 0.0;
+    // chunk load: 8 independent global loads in flight per thread (consecutive threads read consecutive
+    // elements of a row), zero fill past the last row / column
+    {
+      const int total = kWyChunk * np;
+      for (int e0 = threadIdx.x; e0 < total; e0 += kWyThreads * 8) {
+        double val[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * kWyThreads;
+          const int i = e / np, c = e - i * np;
+          const int64_t gr = base + i;
+          val[u] = (e < total && gr < row_hi && c < n) ? (double)A[gr * lda + c] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * kWyThreads;
+          if (e < total) {
+            const int i = e / np, c = e - i * np;
+            C[i * pc + c] = val[u];
+          }
+        }
+      }
     }
     __syncthreads();
     for (int j0 = 0; j0 < np; j0 += 8) {
       if (warp == 0) {
-        // ---- panel factorization: rows lane, lane+32, lane+64, lane+96 of the 128 x 8 panel in registers
+        // ---- panel factorization: rows lane, lane+32, lane+64, lane+96 of the 128 x 8 panel in registers.
+        // Everything a step needs lives in registers (the panel, row j of R, this lane's row of T), so the 8
+        // steps run without a single barrier or shared-memory round trip; the reductions of a step (7 - t
+        // projections onto the other panel columns, t inner products with the earlier reflectors) are
+        // independent butterflies that the scheduler interleaves.
         double x[4][8];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int k = 0; k < 8; ++k) x[r][k] = C[(lane + 32 * r) * pc + j0 + k];
+        double trow[8];                                       // lane s < 8 keeps row s of T
+#pragma unroll
+        for (int q = 0; q < 8; ++q) trow[q] = 0.0;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           double* Rrow = Rp + wy_roff(j0 + t, np);           // Rrow[k - t] = R[j0 + t][j0 + k]
-          double sigma = 0.0;
+          double rr[8];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) sigma += x[r][t] * x[r][t];
-          sigma = warp_sum(sigma);
-          const double alpha = Rrow[0];
+          for (int k = t; k < 8; ++k) rr[k] = Rrow[k - t];
+          // One batch of independent butterflies: p[q] = x_t . (column q).  p[t] is the squared norm that
+          // fixes the reflector; the others are the projections, needed only after scaling (v = scale x_t), so
+          // their reduction latency overlaps the sqrt / reciprocal chain instead of following it.
+          double p[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            p[q] = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) p[q] += x[r][t] * x[r][q];
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) p[q] = warp_sum(p[q]);
+          const double sigma = p[t];
+          const double alpha = rr[t];
           double tau = 0.0, beta = alpha, scale = 0.0;
           if (sigma != 0.0) {                                 // LAPACK dlarfg
             const double nrm = sqrt(alpha * alpha + sigma);
             beta = alpha >= 0.0 ? -nrm : nrm;
-            tau = (beta - alpha) / beta;
+            const double inv_beta = 1.0 / beta;
             scale = 1.0 / (alpha - beta);
+            tau = (beta - alpha) * inv_beta;
           }
           double v[4];
 #pragma unroll
           for (int r = 0; r < 4; ++r) v[r] = x[r][t] * scale;
-          __syncwarp();
+          double d[8];                                        // v . (column q): q < t -> Vc^T Vc, q > t -> projections
+#pragma unroll
+          for (int q = 0; q < 8; ++q) d[q] = scale * p[q];
 #pragma unroll
           for (int k = t + 1; k < 8; ++k) {                   // H_t on the rest of the panel
-            double w = 0.0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) w += v[r] * x[r][k];
-            w = warp_sum(w);
-            const double tw = tau * (w + Rrow[k - t]);
+            const double tw = tau * (d[k] + rr[k]);
 #pragma unroll
             for (int r = 0; r < 4; ++r) x[r][k] -= tw * v[r];
-            __syncwarp();
-            if (lane == 0) Rrow[k - t] -= tw;
-          }
-          double g[8];                                        // (Vc^T Vc)[s][t], s < t
-#pragma unroll
-          for (int q = 0; q < 8; ++q) g[q] = 0.0;
-#pragma unroll
-          for (int q = 0; q < t; ++q) {
-            double d = 0.0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) d += x[r][q] * v[r];
-            g[q] = warp_sum(d);
+            rr[k] -= tw;
           }
 #pragma unroll
           for (int r = 0; r < 4; ++r) x[r][t] = v[r];
-          // T(0:t-1, t) = -tau T(0:t-1, 0:t-1) g ; T(t, t) = tau          (dlarft, forward columnwise)
-          if (lane < t) {
-            double acc = 0.0;
+          // T(0:t-1, t) = -tau T(0:t-1, 0:t-1) (Vc^T Vc)(0:t-1, t) ; T(t, t) = tau     (dlarft, forward columnwise)
+          double acc = 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (u >= lane && u < t) acc += Tm[lane * 8 + u] * g[u];
-            Tm[lane * 8 + t] = -tau * acc;
-          }
+          for (int u = 0; u < t; ++u)
+            if (u >= lane) acc += trow[u] * d[u];
+          trow[t] = lane < t ? -tau * acc : (lane == t ? tau : 0.0);
           if (lane == 0) {
-            Tm[t * 8 + t] = tau;
             Rrow[0] = beta;
+#pragma unroll
+            for (int k = t + 1; k < 8; ++k) Rrow[k - t] = rr[k];
           }
-          __syncwarp();
+        }
+        if (lane < 8) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) Tm[lane * 8 + q] = trow[q];
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
