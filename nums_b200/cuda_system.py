@@ -79,6 +79,9 @@ class CudaSystem(object):
                 continue
             self.remote_functions[name] = fn
             self.methods[name] = self._make_callable(name)
+        if "bop" in self.remote_functions:
+            self._bop_kernel = self.remote_functions["bop"]
+            self.methods["bop"] = self._call_bop          # the per-block hot call: a leaner copy of ``call``
         # optional kernels beyond the 28 interface methods (fused logistic-regression step)
         for name, fn in getattr(self.compute_module, "EXTRA_KERNELS", {}).items():
             self.remote_functions[name] = fn
@@ -204,6 +207,26 @@ class CudaSystem(object):
             args = tuple(q.resolve(a) for a in args)
             kwargs = {k: q.resolve(v) for k, v in kwargs.items()}
         return self.remote_functions[name](*args, **kwargs)
+
+    def _call_bop(self, op, a1, a2, a1_shape, a2_shape, a1_T, a2_T, axes=None, syskwargs=None):
+        """``call("bop", ...)`` without the generic argument handling (Block.bop, base.py:220-231, calls with
+        exactly these seven positionals + ``axes`` + ``syskwargs``)."""
+        q = self.contractions
+        if q.enabled:
+            if op == "tensordot":
+                if a1.__class__ is not DeferredContraction and a2.__class__ is not DeferredContraction:
+                    lazy = q.tensordot(a1, a2, a1_shape, a2_shape, a1_T, a2_T, axes)
+                    if lazy is not None:
+                        return lazy
+            elif op == "add" and q._pending and (a1.__class__ is DeferredContraction or a2.__class__ is DeferredContraction):
+                lazy = q.add(a1, a2, a1_shape, a2_shape, a1_T, a2_T)
+                if lazy is not None:
+                    return lazy
+        if a1.__class__ is DeferredContraction:
+            a1 = q.resolve(a1)
+        if a2.__class__ is DeferredContraction:
+            a2 = q.resolve(a2)
+        return self._bop_kernel(op, a1, a2, a1_shape, a2_shape, a1_T, a2_T, axes)
 
     def _try_defer(self, args, kwargs):
         """tensordot -> DeferredContraction; add of deferred contractions -> longer term list."""

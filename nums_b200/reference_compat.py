@@ -141,8 +141,35 @@ def load_reference(system_name="serial"):
     if settings.system_name not in ("serial", "cuda"):
         settings.system_name = system_name
     _register_cuda_system()
+    if os.environ.get("NUMS_HOST_FAST_PATH", "1") != "0":
+        _install_host_fast_path()
     _nums = nums
     return nums
+
+
+def _install_host_fast_path():
+    """SURVEY.md section 8f.2, the part that needs no source edit: the host layers infer every result dtype by
+    running the ufunc on freshly built 0-d arrays (``nums/core/array/utils.py:27-52``) -- once per block per
+    operation, ~8 us each, which is more than a quarter of the per-block dispatch budget when the kernel itself
+    takes ~40 us (config 1).  The three helpers are pure functions of (op name, dtype[s]); they are replaced by
+    memoised versions of themselves.  Results are identical by construction (the original function computes
+    every cache entry)."""
+    import functools
+    from nums.core.array import utils as array_utils
+    for name in ("get_bop_output_type", "get_uop_output_type", "get_reduce_output_type"):
+        fn = getattr(array_utils, name)
+        if getattr(fn, "_nums_b200", False):
+            continue
+        cached = functools.lru_cache(maxsize=None)(fn)
+
+        def wrapper(*args, _cached=cached, _fn=fn):
+            try:
+                return _cached(*args)
+            except TypeError:            # unhashable argument: fall through to the original
+                return _fn(*args)
+        wrapper._nums_b200 = True
+        wrapper.__name__ = name
+        setattr(array_utils, name, wrapper)
 
 
 def _register_cuda_system():

@@ -475,6 +475,7 @@ class SpmdSystem(object):
         self.rng_cls = getattr(local, "rng_cls", None)
         self._registered = set()
         self._next = 0
+        self._bop_meta = {}
         self._owners = {}
         self._lazies = []
         self._copied = weakref.WeakSet()      # handles with cached copies away from home
@@ -867,6 +868,37 @@ class SpmdSystem(object):
                 hint = self._hint(sysk)
                 items = [("blk", a1, a1.home), ("blk", a2, a2.home)]
                 return self._lazy_handle(items, 0 if hint is None else hint, a1.shape, _F64)
+        # elementwise on operands that already sit together (config 1, the Newton iteration's vector algebra):
+        # the executing rank and the result's shape / dtype follow without the generic machinery
+        if a1.lazy is None and a2.lazy is None and not a1.copies and not a2.copies:
+            h1, h2 = a1.home, a2.home
+            if h1 == h2:
+                e = h1
+            elif h1 == REPLICATED:
+                e = h2
+            elif h2 == REPLICATED:
+                e = h1
+            else:
+                return _NOT_HANDLED
+            if e == REPLICATED:
+                return _NOT_HANDLED
+            key = (op, a1.dtype, a2.dtype, tuple(s1), tuple(s2))
+            meta = self._bop_meta.get(key)
+            if meta is None:
+                desc = infer_result("bop", (op, a1, a2, s1, s2, t1, t2, axes), {}, self._meta_of)
+                if desc is None or desc[0] != "b":
+                    return _NOT_HANDLED
+                meta = (desc[1], np.dtype(desc[2]))
+                if len(self._bop_meta) < 4096:
+                    self._bop_meta[key] = meta
+            value = None
+            if e == self.rank:
+                self.stats["executed"] += 1
+                value = self.local.call("bop", op, a1.value, a2.value, s1, s2, t1, t2, axes=axes)
+            else:
+                self.stats["skipped"] += 1
+            self._next += 1
+            return Handle._make(self._next, e, value, meta[0], meta[1])
         return _NOT_HANDLED
 
     def flush(self):
