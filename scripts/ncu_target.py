@@ -38,6 +38,16 @@ elif which == "lr":
     beta = torch.randn(d, dtype=torch.float64, device=dev) / 5
     for _ in range(4):
         out = cc.lr_grad_hess(X, y, beta)
+elif which == "qrh":          # the Householder leaf (blocked WY / DMMA kernel) on one config-3 block
+    X = torch.randn((2_097_152, 128), dtype=torch.float64, device=dev)
+    for _ in range(2):
+        r = cc._householder_r(X)
+elif which == "rowcol":       # (n, 1) * (n, 28): the s * X of the LR Hessian (glms.py:236) on one config-4 block
+    n, d = 1_375_000, 28
+    X = torch.randn((n, d), dtype=torch.float64, device=dev)
+    col = torch.randn((n, 1), dtype=torch.float64, device=dev)
+    for _ in range(4):
+        w = system.bop("mul", col, X, (n, 1), (n, d), False, False, axes=None, syskwargs={})
 elif which == "qr":
     X = torch.randn((262144, 128), dtype=torch.float64, device=dev)
     for _ in range(2):
