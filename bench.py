@@ -364,6 +364,19 @@ def other_workloads(host, quick):
         "workload": "Newton iteration = fused gradient+Hessian kernel + fused update kernel, 11M x 28 float64, 8 row blocks, "
                     "10 iterations, one 16-byte read-back each",
         "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_fused) / 1e9}
+    if host.kind == "reference":
+        from nums_b200 import glms_fused
+
+        def fused_glms():
+            beta0 = app.zeros((d,), (d,), np.float64)
+            host.launch(glms_fused.newton(app, model, beta0, X, y, app.scalar(0.0), iters_fused))
+        t = timed(fused_glms, 2 if quick else 3)
+        out["newton_lr_fused_glms"] = {
+            "value": t / iters_fused, "unit": "s/iter",
+            "workload": "nums_b200.glms_fused.newton (the drop-in for glms.newton: lr_grad_hess per block + sum_reduce + "
+                        "newton_step through the kernel interface, status read one iteration late), 11M x 28 float64, "
+                        "8 row blocks, 10 iterations",
+            "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_fused) / 1e9}
     del X, y, xs, ys
 
     # cfg3: TSQR 16M x 128 (17.2 GB), 8 row blocks: R only, and (Q, R)
@@ -583,6 +596,20 @@ def api_workloads(host, quick):
         "workload": "glms.newton on 11M x 28 float64, 8 row blocks over %d GPU(s) through SpmdSystem: ~15 kernel calls per block "
                     "per iteration on the block's owner, g and H all-reduced, beta replicated" % world,
         "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters) / 1e9}
+    from nums_b200 import glms_fused
+    iters_fused = 10
+
+    def fused_glms():
+        beta0 = app.zeros((d,), (d,), np.float64)
+        host.launch(glms_fused.newton(app, model, beta0, X, y, app.scalar(0.0), iters_fused))
+        torch.cuda.synchronize()
+    t = timed(fused_glms, 2 if quick else 3)
+    out["newton_lr_fused_glms"] = {
+        "value": t / iters_fused, "unit": "s/iter",
+        "workload": "nums_b200.glms_fused.newton through SpmdSystem on %d GPU(s): lr_grad_hess per block on its owner, g | H "
+                    "summed locally and all-reduced (one 812-double NCCL all-reduce per iteration), newton_step replicated, "
+                    "status read one iteration late; 11M x 28 float64, 8 row blocks, 10 iterations" % world,
+        "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_fused) / 1e9}
     del X, y
     torch.cuda.empty_cache()
     if world >= 8 and not quick:

@@ -206,8 +206,11 @@ int launch_bop(const Layout3& L, const nums_array_t* a, const nums_array_t* b,
       return NUMS_OK;
     }
   }
+  // (a 2-D collapsed layout is dense for an operand when its strides are {cols, 1}: the axes could not be merged
+  // only because the OTHER operand is constant along one of them)
+  auto dense2d = [&](int o) { return L.stride[o][1] == 1 && L.stride[o][0] == L.shape[1]; };
   if constexpr (std::is_floating_point<T>::value)     // (the float loops are the ones on the hot path; keeps build time down)
-  if (out_dense && out_al && L.ndim == 2 && n < (int64_t)0x7fffffff && L.shape[1] % VEC == 0) {
+  if (out_al && L.ndim == 2 && dense2d(0) && n < (int64_t)0x7fffffff && L.shape[1] % VEC == 0) {
     // (rows, cols) (+) (rows, 1) / (1, cols): one dense operand, the other constant along one axis
     const unsigned grid = blocks_for(n, kThreads * kUnroll * VEC);
     OS* o = static_cast<OS*>(out->data);
@@ -216,7 +219,7 @@ int launch_bop(const Layout3& L, const nums_array_t* a, const nums_array_t* b,
       const int big_op = 3 - small_op;
       const nums_array_t* big = big_op == 1 ? a : b;
       const nums_array_t* small = small_op == 1 ? a : b;
-      const bool big_dense = (big_op == 1 ? a_dense : b_dense) && aligned16(big->data);
+      const bool big_dense = dense2d(big_op) && (big_op == 1 ? a_same : b_same) && aligned16(big->data);
       if (!big_dense) continue;
       const int64_t s0 = L.stride[small_op][0], s1 = L.stride[small_op][1];
       const bool per_row = s1 == 0 && s0 != 0, per_col = s0 == 0 && s1 != 0;

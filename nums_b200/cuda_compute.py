@@ -727,10 +727,21 @@ class ComputeCls(_ComputeImp):
     def qr(self, *arrays, mode="reduced", axis=None):
         if len(arrays) > 1:
             assert axis is not None
-            arr = concatenate([upload(a) for a in arrays], axis)
+            if mode == "r" and int(axis) == 0 and all(a.__class__ is DeferredR and a.value is None for a in arrays) \
+                    and len({a.shape for a in arrays}) == 1:
+                fused = _fused_stacked_r(list(arrays))        # the stacked-R call of indirect_tsr (application.py:807-814)
+                if fused is not None:
+                    return fused
+            arr = concatenate([a.materialize() if a.__class__ is DeferredR else upload(a) for a in arrays], axis)
+        elif arrays[0].__class__ is DeferredR:
+            arr = arrays[0].materialize()                     # R of a triangular factor: itself
+            if mode == "r":
+                return arr
         else:
             arr = upload(arrays[0])
         if mode == "r":
+            if QR_DEFER_ENABLED and len(arrays) == 1 and arr.dim() == 2 and _gram_path_ok(arr):
+                return DeferredR(_gram_of(arr), arr)
             return qr_r(arr)
         if mode == "reduced":
             return qr_reduced(arr)
@@ -868,7 +879,9 @@ QR_GRAM_MIN_ASPECT = 8        # m >= 8 n
 QR_GRAM_MAX_COLS = 256
 QR_GRAM_ACCEPT_KAPPA = 30.0   # one Cholesky pass: error ~ kappa^2 eps  (< 1e-12)
 QR_GRAM_REFINE_KAPPA = 1.0e6  # two passes (CholeskyQR2) are as good as Householder below ~1e7
-QR_STATS = {"gram": 0, "gram2": 0, "householder": 0}
+QR_STATS = {"gram": 0, "gram2": 0, "householder": 0, "gram_fused": 0}
+# NUMS_QR_DEFER=0: qr(block, mode="r") factors at once instead of handing out a DeferredR
+QR_DEFER_ENABLED = __import__("os").environ.get("NUMS_QR_DEFER", "1") != "0"
 # NUMS_QR_GRAM=0 sends every block through the Householder kernel (measurements, paranoia)
 QR_GRAM_ENABLED = __import__("os").environ.get("NUMS_QR_GRAM", "1") != "0"
 
@@ -925,9 +938,21 @@ def _gram_factor(a):
     which is tight for the nearly diagonal factors of well-conditioned blocks (a Frobenius bound
     would be off by a factor n).  Returns (L, Linv, R, kappa_bound); the bound is inf if the Gram
     matrix is not numerically positive definite.  One 40-byte read-back."""
+    return _factor_gram(_gram_of(a))
+
+
+def _gram_of(a):
+    """a^T a of a tall float64 block on the DMMA GEMM (split-K)."""
     m, n = a.shape
     gram = _empty((n, n), np.float64)
     gemm_into(gram, a, True, n, a, False, n, n, n, m)
+    return gram
+
+
+def _factor_gram(gram):
+    """(L, L^-1, R = L^T, bound on cond_2) from a Gram matrix; see _gram_factor."""
+    n = gram.shape[0]
+    a = gram
     low = _empty((n, n), np.float64)
     stats = _empty((5,), np.float64)
     if n <= GRAM_FACTOR_FUSED_MAX:
@@ -951,7 +976,55 @@ def _gram_factor(a):
     return low, low_inv, upper, float(np.sqrt(bound))
 
 
-def qr_r_ex(arr):
+def _gram_path_ok(arr):
+    m, n = arr.shape
+    return (QR_GRAM_ENABLED and arr.dtype == torch.float64 and arr.is_contiguous() and n % 2 == 0
+            and 2 <= n <= QR_GRAM_MAX_COLS and m >= QR_GRAM_MIN_ASPECT * n and m >= 1024 and arr.data_ptr() % 16 == 0)
+
+
+class DeferredR(object):
+    """The R factor of a tall block that so far exists only as the block's Gram matrix.
+
+    ``indirect_tsr`` (application.py:784-814) asks for one ``qr(block, mode="r")`` per row block and then for the
+    ``qr`` of the stacked R's.  On the Gram path both stages are Cholesky factorizations -- of G_i = X_i^T X_i and of
+    sum_i R_i^T R_i = sum_i G_i -- so the per-block factorizations (a small-matrix kernel and a 40-byte read-back
+    each) are pure overhead when the stacked call follows: ``qr`` hands out this handle instead, the stacked call
+    adds the Gram matrices and factors ONCE, with the condition bound checked on the result.  Anything else that
+    touches the handle (``get``, any other kernel) materialises R_i exactly as before (``qr_r_ex``)."""
+    __slots__ = ("gram", "source", "value", "shape", "__weakref__")
+    dtype = torch.float64
+
+    def __init__(self, gram, source):
+        self.gram, self.source, self.value = gram, source, None
+        n = int(gram.shape[0])
+        self.shape = (n, n)
+
+    def materialize(self):
+        if self.value is None:
+            self.value = qr_r_ex(self.source, self.gram)[0]
+            self.gram = self.source = None
+        return self.value
+
+
+def _fused_stacked_r(parts):
+    """R of the stacked blocks behind ``parts`` (all DeferredR of one width) from the SUM of their Gram matrices;
+    None if the condition bound of the result is not small enough for a single Cholesky pass."""
+    n = parts[0].shape[0]
+    grams = [p.gram for p in parts]
+    if len(grams) == 1:
+        total = grams[0]
+    else:
+        total = _empty((n, n), np.float64)
+        ptrs = (_lib.ctypes.c_void_p * len(grams))(*[g.data_ptr() for g in grams])
+        LIB.check(LIB.dll.nums_sum_reduce(len(grams), ptrs, _lib.F64, n * n, total.data_ptr(), _stream()))
+    _low, _low_inv, upper, kappa = _factor_gram(total)
+    if kappa <= QR_GRAM_ACCEPT_KAPPA:
+        QR_STATS["gram_fused"] += 1
+        return upper
+    return None
+
+
+def qr_r_ex(arr, gram=None):
     """(R, kappa_bound).  R is the k x n (k = min(m, n)) triangular factor of a 2-D block.
 
     Tall float64 blocks go through the Gram matrix: R = chol(A^T A)^T when the condition bound is
@@ -964,11 +1037,9 @@ def qr_r_ex(arr):
     if not arr.is_contiguous():
         arr = _materialize(arr)
     m, n = arr.shape
-    gram_ok = (QR_GRAM_ENABLED and arr.dtype == torch.float64 and n % 2 == 0 and 2 <= n <= QR_GRAM_MAX_COLS
-               and m >= QR_GRAM_MIN_ASPECT * n and m >= 1024 and arr.data_ptr() % 16 == 0)
-    if not gram_ok:
+    if gram is None and not _gram_path_ok(arr):
         return _householder_r(arr), None
-    low, low_inv, upper, kappa = _gram_factor(arr)
+    low, low_inv, upper, kappa = _factor_gram(gram if gram is not None else _gram_of(arr))
     if kappa <= QR_GRAM_ACCEPT_KAPPA:
         QR_STATS["gram"] += 1
         return upper, kappa

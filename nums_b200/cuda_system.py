@@ -122,6 +122,22 @@ class CudaSystem(object):
             return tuple(self.get(o) for o in object_ids)
         return cuda_compute.download(object_ids)
 
+    def get_async(self, oid):
+        """Start fetching a (small) block without blocking: returns a callable that waits for the copy and
+        gives the NumPy array.  Lets a driver loop read a convergence flag one iteration late, with the next
+        iteration already enqueued (nums_b200.glms_fused.newton)."""
+        t = self.contractions.resolve(oid)
+        if not isinstance(t, torch.Tensor):
+            return lambda: t
+        host = cuda_compute._to_pinned(t)
+        done = torch.cuda.Event()
+        done.record()
+
+        def wait():
+            done.synchronize()
+            return host.numpy()
+        return wait
+
     def get_assembled(self, grid, oids_by_entry):
         """Whole array of a block grid as one NumPy array (BlockArrayBase.get, base.py:348-360).
 
@@ -204,9 +220,15 @@ class CudaSystem(object):
                 if lazy is not None:
                     return lazy
         if q._pending or q.materialized_seen:
-            args = tuple(q.resolve(a) for a in args)
+            if name == "qr":         # the stacked-R call consumes DeferredR handles as they are (cuda_compute.DeferredR)
+                args = tuple(a if a.__class__ is cuda_compute.DeferredR else q.resolve(a) for a in args)
+            else:
+                args = tuple(q.resolve(a) for a in args)
             kwargs = {k: q.resolve(v) for k, v in kwargs.items()}
-        return self.remote_functions[name](*args, **kwargs)
+        out = self.remote_functions[name](*args, **kwargs)
+        if out.__class__ is cuda_compute.DeferredR:
+            q.materialized_seen = True
+        return out
 
     def _call_bop(self, op, a1, a2, a1_shape, a2_shape, a1_T, a2_T, axes=None, syskwargs=None):
         """``call("bop", ...)`` without the generic argument handling (Block.bop, base.py:220-231, calls with
@@ -222,9 +244,9 @@ class CudaSystem(object):
                 lazy = q.add(a1, a2, a1_shape, a2_shape, a1_T, a2_T)
                 if lazy is not None:
                     return lazy
-        if a1.__class__ is DeferredContraction:
+        if a1.__class__ is not torch.Tensor:          # deferred contraction / deferred R factor / host value
             a1 = q.resolve(a1)
-        if a2.__class__ is DeferredContraction:
+        if a2.__class__ is not torch.Tensor:
             a2 = q.resolve(a2)
         return self._bop_kernel(op, a1, a2, a1_shape, a2_shape, a1_T, a2_T, axes)
 

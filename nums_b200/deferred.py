@@ -178,9 +178,11 @@ class ContractionQueue(object):
             if obj.value is None:
                 self.flush()
             return obj.value
+        if obj.__class__ is cuda_compute.DeferredR:          # an R factor still held as a Gram matrix
+            return obj.materialize()
         if isinstance(obj, list):
             return [self.resolve(o) for o in obj]
-        if isinstance(obj, tuple) and any(isinstance(o, DeferredContraction) for o in obj):
+        if isinstance(obj, tuple) and any(isinstance(o, (DeferredContraction, cuda_compute.DeferredR)) for o in obj):
             return tuple(self.resolve(o) for o in obj)
         return obj
 

@@ -48,16 +48,35 @@ def newton(app, model, beta, X, y, tol, max_iter):
     tol_value = float(np.asarray(tol.get() if hasattr(tol, "get") else tol))
     one = {"grid_entry": (0,), "grid_shape": (1,)}
     beta_oid = beta.blocks[0].oid
+    get_async = getattr(system, "get_async", None)
+    pending = None            # (beta after that iteration, waiter for its {max |g|, info})
+
+    def converged(entry):
+        gmax, info = (float(v) for v in np.asarray(entry[1]()))
+        if info != 0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        return gmax <= tol_value
+
     for _ in range(max_iter):
         parts = [system.lr_grad_hess(X.blocks[i, 0].oid, y.blocks[i].oid, beta_oid,
                                      syskwargs={"grid_entry": (i, 0), "grid_shape": (G, 1)}) for i in range(G)]
         gh = parts[0] if G == 1 else system.sum_reduce(*parts, syskwargs=one)
         beta_oid, status = system.newton_step(gh, beta_oid, syskwargs=one)
-        gmax, info = (float(v) for v in np.asarray(system.get(status)))       # the one host sync per iteration
-        if info != 0:
-            raise np.linalg.LinAlgError("Singular matrix")
-        if gmax <= tol_value:
+        # The convergence test of iteration i (glms.py:370) is read one iteration late: iteration i + 1 is already
+        # enqueued when the host looks at the 16 status bytes of iteration i, so the device never idles on the
+        # read-back.  If iteration i had converged, its beta is returned and the speculative step is dropped --
+        # the same value the reference's loop returns.
+        if get_async is None:
+            waiter = (lambda v: (lambda: v))(system.get(status))
+        else:
+            waiter = get_async(status)
+        if pending is not None and converged(pending):
+            beta_oid = pending[0]
+            pending = None
             break
+        pending = (beta_oid, waiter)
+    if pending is not None:
+        converged(pending)       # surfaces a singular Hessian of the last iteration
     return BlockArray.from_oid(beta_oid, (d,), np.float64, system)
 
 

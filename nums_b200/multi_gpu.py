@@ -553,17 +553,29 @@ def newton_lr(system, comm, x_blocks, y_blocks, d, tol, max_iter, grad_hess, ste
                             syskwargs={"grid_entry": (0,), "grid_shape": (1,)})
     sk = {"grid_entry": (0,), "grid_shape": (1,)}
     iters = 0
+    get_async = getattr(system, "get_async", None)
+    pending = None           # (beta after that iteration, its iteration number, waiter for {max |g|, info})
+
+    def converged(entry):
+        gmax, info = (float(v) for v in np.asarray(entry[2]()))
+        if info != 0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        return gmax <= tol
+
     for _ in range(max_iter):
         iters += 1
         acc = grad_hess(x_blocks, y_blocks, beta)    # g | H summed over this rank's row blocks
         comm.all_reduce_sum(acc)
         if step is not None:
             beta, status = step(acc, beta)
-            gmax, info = (float(v) for v in np.asarray(system.get(status)))     # the one host sync per iteration
-            if info != 0:
-                raise np.linalg.LinAlgError("Singular matrix")
-            if gmax <= tol:
+            # the status of iteration i is read after iteration i + 1 has been enqueued (no device idle time on the
+            # 16-byte read-back); a converged iteration's beta is returned and the speculative step dropped
+            waiter = get_async(status) if get_async is not None else (lambda v: (lambda: v))(system.get(status))
+            if pending is not None and converged(pending):
+                beta, iters = pending[0], pending[1]
+                pending = None
                 break
+            pending = (beta, iters, waiter)
             continue
         g = acc[:d]
         h = acc[d:].reshape(d, d) if isinstance(acc, np.ndarray) else acc[d:].view(d, d)
@@ -573,4 +585,6 @@ def newton_lr(system, comm, x_blocks, y_blocks, d, tol, max_iter, grad_hess, ste
         gmax = system.reduce_axis("max", system.map_uop("abs", g, (), {}, syskwargs=sk), None, False, False, syskwargs=sk)
         if float(np.asarray(system.get(gmax))) <= tol:     # the one host sync per iteration
             break
+    if pending is not None:
+        converged(pending)
     return beta, iters

@@ -105,8 +105,9 @@ class _TorchBackend(object):
 
     def is_block(self, v):
         import torch
+        from nums_b200.cuda_compute import DeferredR
         from nums_b200.deferred import DeferredContraction
-        return isinstance(v, (torch.Tensor, DeferredContraction))
+        return isinstance(v, (torch.Tensor, DeferredContraction, DeferredR))
 
     def concrete(self, v):
         """A dense tensor holding the block (launches whatever the local system still defers)."""
@@ -701,6 +702,15 @@ class SpmdSystem(object):
         local_values = walk(oids)
         return self.local.get(local_values)
 
+    def get_async(self, oid):
+        """``CudaSystem.get_async`` for a replicated block (every rank reads its own copy); other blocks are
+        fetched synchronously."""
+        self.flush()
+        if isinstance(oid, Handle) and oid.home == REPLICATED and hasattr(self.local, "get_async"):
+            return self.local.get_async(oid.value)
+        value = self.get(oid)
+        return lambda: value
+
     def _fetch(self, h):
         """The block of ``h`` on THIS rank (broadcast from its home when it is not replicated)."""
         if h.home == REPLICATED:
@@ -1057,6 +1067,38 @@ class SpmdSystem(object):
         self.stats["all_reduces"] += 1
         return self._new_handle(REPLICATED, part, first.shape, first.dtype)
 
+    def _fused_gram_qr(self, args, where, n, dt):
+        """Stacked-R ``qr`` when every per-block R is still a ``cuda_compute.DeferredR`` (a Gram matrix): the
+        Gram matrices are summed where they are, all-reduced (n*n + 2 doubles, the last two counting blocks so
+        that every rank learns whether ALL blocks were deferred) and factored once on every rank -- one
+        collective and one small-matrix kernel instead of per-block factorizations plus a tree of stacked QRs.
+        None (no collective issued) on the CPU back end; None after the all-reduce when a block was not deferred
+        or the condition bound of the sum is too large, in which case the tree below takes over."""
+        if not isinstance(self.backend, _TorchBackend) or dt != _F64:
+            return None
+        import torch
+        from nums_b200 import cuda_compute as cc
+        from nums_b200._lib import LIB
+        mine = [h.value for h, w in zip(args, where) if w == self.rank]
+        deferred = [v for v in mine if v.__class__ is cc.DeferredR and v.value is None and v.shape == (n, n)]
+        buf = self.backend.zeros((n * n + 2,), np.float64)
+        if mine:
+            if len(deferred) == len(mine):
+                ptrs = (cc._lib.ctypes.c_void_p * len(deferred))(*[v.gram.data_ptr() for v in deferred])
+                LIB.check(LIB.dll.nums_sum_reduce(len(deferred), ptrs, cc._lib.F64, n * n, buf.data_ptr(), cc._stream()))
+            counts = torch.tensor([float(len(deferred)), float(len(mine))], dtype=torch.float64)
+            buf[n * n:].copy_(counts.to(buf.device, non_blocking=True))
+        self.comm.all_reduce_sum(buf)
+        self.stats["all_reduces"] += 1
+        got, total = (float(v) for v in buf[n * n:].cpu())
+        if got != total:
+            return None
+        _low, _low_inv, upper, kappa = cc._factor_gram(buf[:n * n].view(n, n))
+        if kappa > cc.QR_GRAM_ACCEPT_KAPPA:
+            return None
+        cc.QR_STATS["gram_fused"] += 1
+        return self._new_handle(REPLICATED, upper, (n, n), dt)
+
     # -- stacked-R qr over blocks living on several ranks: local QR, binary tree, broadcast ---------------
     def _k_qr(self, args, kwargs, sysk):
         mode, axis = kwargs.get("mode", "reduced"), kwargs.get("axis")
@@ -1075,6 +1117,9 @@ class SpmdSystem(object):
         where = [h.home if h.home != REPLICATED else anchor for h in args]
         ranks = sorted(set(where))
         rows = {r: min(sum(h.shape[0] for h, w in zip(args, where) if w == r), n) for r in ranks}
+        fused = self._fused_gram_qr(args, where, n, dt)
+        if fused is not None:
+            return fused
         r_local = None
         if self.rank in ranks:
             mine = [h.value for h, w in zip(args, where) if w == self.rank]

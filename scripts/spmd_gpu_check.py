@@ -115,6 +115,12 @@ def main():
         if np.max(np.abs(g)) <= 1e-8:
             break
     checks["beta_rel"] = rel(beta, ref)
+    # the same fit through the fused kernels behind glms (one lr_grad_hess per block on its owner, g | H all-reduced)
+    from nums_b200 import glms_fused
+    moved = system.stats["moved_bytes"]
+    beta_f = glms_fused.newton(app, model, app.zeros((d,), (d,), dtype=np.float64), Xn, yn, app.scalar(1e-8), 8).get()
+    checks["fused_lr_moved_bytes"] = system.stats["moved_bytes"] - moved
+    checks["fused_beta_rel"] = rel(beta_f, ref)
 
     # carried state / dynamic sizes
     vals = rng.standard_normal(100_000)
@@ -128,7 +134,8 @@ def main():
           and checks["gram_rel"] <= 1e-10 and checks["sum_axis0_rel"] <= 1e-12 and checks["max_exact"]
           and checks["sum_all_rel"] <= 1e-12 and checks["R_replicated"] and checks["R_rel"] <= 1e-10
           and checks["QR_rel"] <= 1e-12 and checks["Q_orth"] <= 1e-10 and checks["lr_moved_bytes"] == 0
-          and checks["beta_rel"] <= 1e-10 and checks["argmax_exact"] and checks["where_exact"])
+          and checks["beta_rel"] <= 1e-10 and checks["fused_beta_rel"] <= 1e-10 and checks["fused_lr_moved_bytes"] == 0
+          and checks["argmax_exact"] and checks["where_exact"])
     flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     all_ok = bool(int(flag.item()))
