@@ -299,12 +299,26 @@ def cuda_time(fn, sync):
     return start.elapsed_time(end) * 1e-3
 
 
-def other_workloads(host, quick):
+def _guarded(out, name, fn):
+    """Run one secondary workload; a failure is recorded under its name instead of costing the whole line."""
+    import gc
+    import traceback
+    import torch
+    try:
+        fn()
+    except Exception as exc:  # noqa: BLE001 -- reported in the JSON line, the other workloads still run
+        out[name] = {"error": "%s: %s" % (type(exc).__name__, exc), "traceback": traceback.format_exc()[-1500:]}
+        sys.stderr.write("[bench] workload %s failed: %s\n" % (name, exc))
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def other_workloads(host, quick, out=None):
     """bop (cfg1), TSQR (cfg3) and Newton LR (cfg4) on one GPU through the host layers `host` (the reference's
     BlockArray / ArrayApplication / glms when installed); device-timed, synthetic data."""
     import torch
     from nums_b200 import cuda_compute as cc
-    out = {}
+    out = {} if out is None else out
     dev = torch.device("cuda", torch.cuda.current_device())
     system, app = host.system, host.app
 
@@ -319,79 +333,88 @@ def other_workloads(host, quick):
     def device_blockarray(shape, block_shape, fill):
         return host.from_blocks(shape, block_shape, lambda _entry, block_shape_: fill(block_shape_))
 
-    # cfg1: u + v, u * v on two 1e8-element vectors in 8 blocks (24 B / element)
-    n = 100_000_000
-    U = device_blockarray((n,), (n // 8,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
-    V = device_blockarray((n,), (n // 8,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
-    for name, fn in (("add", lambda: host.launch(U + V)), ("mul", lambda: host.launch(U * V))):
-        t = timed(fn, 5 if quick else 20)
-        out["bop_" + name] = {"value": 24.0 * n / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
-                              "workload": "float64 %s of two 1e8-element BlockArrays, 8 blocks (inputs 1.6 GB > L2)" % name}
-    del U, V
+    def cfg1():
+        # u + v, u * v on two 1e8-element vectors in 8 blocks (24 B / element)
+        n = 100_000_000
+        U = device_blockarray((n,), (n // 8,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
+        V = device_blockarray((n,), (n // 8,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
+        for name, fn in (("add", lambda: host.launch(U + V)), ("mul", lambda: host.launch(U * V))):
+            t = timed(fn, 5 if quick else 20)
+            out["bop_" + name] = {"value": 24.0 * n / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
+                                  "workload": "float64 %s of two 1e8-element BlockArrays, 8 blocks (inputs 1.6 GB > L2)" % name}
 
-    # cfg4: Newton LR 11M x 28, 8 row blocks
-    N, d, G = 11_000_000, 28, 8
-    nb_rows = N // G
-    X = device_blockarray((N, d), (nb_rows, d), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
-    theta = torch.randn(d, dtype=torch.float64, device=dev) / np.sqrt(d)
-    y = host.blockarray((N,), (nb_rows,), "float64")
-    for (i,) in y.grid.get_entry_iterator():
-        xb = X.blocks[i, 0].oid
-        p = torch.sigmoid(xb @ theta)
-        y.blocks[i].oid = (torch.rand(xb.shape[0], dtype=torch.float64, device=dev) < p).to(torch.float64)
-    model = host.logistic_model()
-    iters_unfused = 2 if quick else 4
+    def cfg4():
+        # Newton LR 11M x 28, 8 row blocks
+        N, d, G = 11_000_000, 28, 8
+        nb_rows = N // G
+        X = device_blockarray((N, d), (nb_rows, d), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
+        theta = torch.randn(d, dtype=torch.float64, device=dev) / np.sqrt(d)
+        y = host.blockarray((N,), (nb_rows,), "float64")
+        for (i,) in y.grid.get_entry_iterator():
+            xb = X.blocks[i, 0].oid
+            p = torch.sigmoid(xb @ theta)
+            y.blocks[i].oid = (torch.rand(xb.shape[0], dtype=torch.float64, device=dev) < p).to(torch.float64)
+        model = host.logistic_model()
+        iters_unfused = 2 if quick else 6
 
-    def unfused():
-        host.launch(host.newton(model, X, y, 1e-300, iters_unfused))
-    t = timed(unfused, 1 if quick else 2)
-    out["newton_lr_interface_path"] = {
-        "value": t / iters_unfused, "unit": "s/iter",
-        "workload": "glms.newton (~15 kernel calls per block per iteration) on 11M x 28 float64, 8 row blocks, host layers: "
-                    + host.kind,
-        "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_unfused) / 1e9}
-    from nums_b200 import multi_gpu
-    comm = multi_gpu.Comm()
-    xs = [X.blocks[i, 0].oid for i in range(G)]
-    ys = [y.blocks[i].oid for i in range(G)]
-    iters_fused = 10
+        def unfused():
+            host.launch(host.newton(model, X, y, 1e-300, iters_unfused))
+        t = timed(unfused, 1 if quick else 3)
+        out["newton_lr_interface_path"] = {
+            "value": t / iters_unfused, "unit": "s/iter",
+            "workload": "glms.newton (~15 kernel calls per block per iteration) on 11M x 28 float64, 8 row blocks, host layers: "
+                        + host.kind,
+            "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_unfused) / 1e9,
+            "unfused_traffic_GBps": 14.8e9 / (t / iters_unfused) / 1e9,
+            "note": "the unfused call sequence streams X about six times per iteration (14.8 GB, SURVEY.md 8d); "
+                    "unfused_traffic_GBps divides that figure by the time"}
+        from nums_b200 import multi_gpu
+        comm = multi_gpu.Comm()
+        xs = [X.blocks[i, 0].oid for i in range(G)]
+        ys = [y.blocks[i].oid for i in range(G)]
+        iters_fused = 10
 
-    def fused():
-        multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters_fused, cc.lr_grad_hess_blocks, step=cc.newton_step)
-    t = timed(fused, 2 if quick else 3)
-    out["newton_lr_fused"] = {
-        "value": t / iters_fused, "unit": "s/iter",
-        "workload": "Newton iteration = fused gradient+Hessian kernel + fused update kernel, 11M x 28 float64, 8 row blocks, "
-                    "10 iterations, one 16-byte read-back each",
-        "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_fused) / 1e9}
-    if host.kind == "reference":
-        from nums_b200 import glms_fused
-
-        def fused_glms():
-            beta0 = app.zeros((d,), (d,), np.float64)
-            host.launch(glms_fused.newton(app, model, beta0, X, y, app.scalar(0.0), iters_fused))
-        t = timed(fused_glms, 2 if quick else 3)
-        out["newton_lr_fused_glms"] = {
+        def fused():
+            multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters_fused, cc.lr_grad_hess_blocks, step=cc.newton_step)
+        t = timed(fused, 2 if quick else 3)
+        out["newton_lr_fused"] = {
             "value": t / iters_fused, "unit": "s/iter",
-            "workload": "nums_b200.glms_fused.newton (the drop-in for glms.newton: lr_grad_hess per block + sum_reduce + "
-                        "newton_step through the kernel interface, status read one iteration late), 11M x 28 float64, "
-                        "8 row blocks, 10 iterations",
+            "workload": "Newton iteration = fused gradient+Hessian kernel + fused update kernel, 11M x 28 float64, 8 row blocks, "
+                        "10 iterations, one 16-byte read-back each",
             "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_fused) / 1e9}
-    del X, y, xs, ys
+        if host.kind == "reference":
+            from nums_b200 import glms_fused
 
-    # cfg3: TSQR 16M x 128 (17.2 GB), 8 row blocks: R only, and (Q, R)
-    m, ncol, G = 16_777_216, 128, 8
-    X = device_blockarray((m, ncol), (m // G, ncol), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
-    flops_r = 2.0 * m * ncol ** 2 - 2.0 * ncol ** 3 / 3.0
-    t = timed(lambda: host.launch(app.indirect_tsr(X)), 1 if quick else 3)
-    out["tsqr_r"] = {"value": flops_r / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
-                     "workload": "indirect_tsr on 16777216 x 128 float64, 8 row blocks (2mn^2 - 2n^3/3 flop)"}
-    t = timed(lambda: host.launch(app.indirect_tsqr(X)[0]), 1 if quick else 3)
-    out["tsqr_qr"] = {"value": (flops_r + 2.0 * m * ncol ** 2) / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
-                      "workload": "indirect_tsqr (Q = X R^-1, R) on 16777216 x 128 float64, 8 row blocks"}
-    del X
-    torch.cuda.empty_cache()
-    out["csv_ingest"] = csv_workload(system, quick)
+            def fused_glms():
+                beta0 = app.zeros((d,), (d,), np.float64)
+                host.launch(glms_fused.newton(app, model, beta0, X, y, app.scalar(0.0), iters_fused))
+            t = timed(fused_glms, 2 if quick else 3)
+            out["newton_lr_fused_glms"] = {
+                "value": t / iters_fused, "unit": "s/iter",
+                "workload": "nums_b200.glms_fused.newton (the drop-in for glms.newton: lr_grad_hess per block + sum_reduce + "
+                            "newton_step through the kernel interface, status read one iteration late), 11M x 28 float64, "
+                            "8 row blocks, 10 iterations",
+                "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_fused) / 1e9}
+
+    def cfg3():
+        # TSQR 16M x 128 (17.2 GB), 8 row blocks: R only, and (Q, R)
+        m, ncol, G = 16_777_216, 128, 8
+        X = device_blockarray((m, ncol), (m // G, ncol), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
+        flops_r = 2.0 * m * ncol ** 2 - 2.0 * ncol ** 3 / 3.0
+        t = timed(lambda: host.launch(app.indirect_tsr(X)), 1 if quick else 3)
+        out["tsqr_r"] = {"value": flops_r / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
+                         "workload": "indirect_tsr on 16777216 x 128 float64, 8 row blocks (2mn^2 - 2n^3/3 flop)"}
+        t = timed(lambda: host.launch(app.indirect_tsqr(X)[0]), 1 if quick else 3)
+        out["tsqr_qr"] = {"value": (flops_r + 2.0 * m * ncol ** 2) / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
+                          "workload": "indirect_tsqr (Q = X R^-1, R) on 16777216 x 128 float64, 8 row blocks"}
+
+    def csv():
+        out["csv_ingest"] = csv_workload(system, quick)
+
+    _guarded(out, "bop", cfg1)
+    _guarded(out, "newton_lr", cfg4)
+    _guarded(out, "tsqr", cfg3)
+    _guarded(out, "csv_ingest", csv)
     return out
 
 
@@ -451,7 +474,7 @@ def csv_workload(system, quick):
             "parity": "first and last 4000 rows bit-identical to the generated doubles"}
 
 
-def sharded_workloads(system, comm, quick):
+def sharded_workloads(system, comm, quick, out=None):
     """bop / TSQR / Newton LR with the block grid dealt over the ranks: elementwise work is
     shard-local, TSQR reduces R over a send/recv tree, Newton LR all-reduces g | H once per iteration.
     Every figure is the whole job (all ranks), timed on the device, max over ranks."""
@@ -461,7 +484,9 @@ def sharded_workloads(system, comm, quick):
     from nums_b200 import multi_gpu
     dev = torch.device("cuda", torch.cuda.current_device())
     world, rank = comm.world, comm.rank
-    out = {}
+    out = {} if out is None else out
+    G = 8
+    mine = [i for i in range(G) if i % world == rank]
 
     def timed(fn, iters):
         fn()
@@ -475,67 +500,68 @@ def sharded_workloads(system, comm, quick):
             times.append(float(t.item()))
         return float(np.median(times))
 
-    # cfg1: 8 blocks of 12.5M, round robin
-    n, G = 100_000_000, 8
-    mine = [i for i in range(G) if i % world == rank]
-    us = [torch.rand(n // G, dtype=torch.float64, device=dev) for _ in mine]
-    vs = [torch.rand(n // G, dtype=torch.float64, device=dev) for _ in mine]
-    shape = (n // G,)
+    def cfg1():
+        # 8 blocks of 12.5M, round robin
+        n = 100_000_000
+        us = [torch.rand(n // G, dtype=torch.float64, device=dev) for _ in mine]
+        vs = [torch.rand(n // G, dtype=torch.float64, device=dev) for _ in mine]
+        shape = (n // G,)
 
-    def bop_add():
-        for u, v, i in zip(us, vs, mine):
-            system.bop("add", u, v, shape, shape, False, False, axes=None, syskwargs={"grid_entry": (i,), "grid_shape": (G,)})
-        torch.cuda.synchronize()
-    t = timed(bop_add, 5 if quick else 20)
-    out["bop_add"] = {"value": 24.0 * n / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
-                      "workload": "float64 add of two 1e8-element arrays, 8 blocks dealt over %d GPU(s), no exchange" % world}
-    del us, vs
+        def bop_add():
+            for u, v, i in zip(us, vs, mine):
+                system.bop("add", u, v, shape, shape, False, False, axes=None, syskwargs={"grid_entry": (i,), "grid_shape": (G,)})
+            torch.cuda.synchronize()
+        t = timed(bop_add, 5 if quick else 20)
+        out["bop_add"] = {"value": 24.0 * n / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
+                          "workload": "float64 add of two 1e8-element arrays, 8 blocks dealt over %d GPU(s), no exchange" % world}
 
-    # cfg3: TSQR 16M x 128, 8 row blocks
-    m, ncol = 16_777_216, 128
-    xs = [torch.randn((m // G, ncol), dtype=torch.float64, device=dev) for _ in mine]
-    flops_r = 2.0 * m * ncol ** 2 - 2.0 * ncol ** 3 / 3.0
+    def cfg3():
+        # TSQR 16M x 128, 8 row blocks
+        m, ncol = 16_777_216, 128
+        xs = [torch.randn((m // G, ncol), dtype=torch.float64, device=dev) for _ in mine]
+        flops_r = 2.0 * m * ncol ** 2 - 2.0 * ncol ** 3 / 3.0
 
-    def tsqr_r():
-        multi_gpu.tsqr_r_tree(system, comm, xs, ncol)
-        torch.cuda.synchronize()
-    t = timed(tsqr_r, 2 if quick else 3)
-    out["tsqr_r"] = {"value": flops_r / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
-                     "workload": "R of 16777216 x 128 float64, 8 row blocks over %d GPU(s), binary tree over the per-rank R" % world}
+        def tsqr_r():
+            multi_gpu.tsqr_r_tree(system, comm, xs, ncol)
+            torch.cuda.synchronize()
+        t = timed(tsqr_r, 2 if quick else 3)
+        out["tsqr_r"] = {"value": flops_r / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
+                         "workload": "R of 16777216 x 128 float64, 8 row blocks over %d GPU(s), binary tree over the per-rank R" % world}
 
-    def tsqr_qr():
-        r = multi_gpu.tsqr_r_tree(system, comm, xs, ncol)
-        r_inv = system.inv(r, syskwargs={"grid_entry": (0, 0), "grid_shape": (1, 1)})
-        qs = [multi_gpu.tsqr_q(system, x, r_inv, (i, 0), (G, 1)) for x, i in zip(xs, mine)]
-        system.flush()
-        torch.cuda.synchronize()
-        return qs
-    t = timed(tsqr_qr, 2 if quick else 3)
-    out["tsqr_qr"] = {"value": (flops_r + 2.0 * m * ncol ** 2) / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
-                      "workload": "(Q = X R^-1, R) of 16777216 x 128 float64 over %d GPU(s)" % world}
-    del xs
-    torch.cuda.empty_cache()
+        def tsqr_qr():
+            r = multi_gpu.tsqr_r_tree(system, comm, xs, ncol)
+            r_inv = system.inv(r, syskwargs={"grid_entry": (0, 0), "grid_shape": (1, 1)})
+            qs = [multi_gpu.tsqr_q(system, x, r_inv, (i, 0), (G, 1)) for x, i in zip(xs, mine)]
+            system.flush()
+            torch.cuda.synchronize()
+            return qs
+        t = timed(tsqr_qr, 2 if quick else 3)
+        out["tsqr_qr"] = {"value": (flops_r + 2.0 * m * ncol ** 2) / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
+                          "workload": "(Q = X R^-1, R) of 16777216 x 128 float64 over %d GPU(s)" % world}
 
-    # cfg4: Newton LR 11M x 28, 8 row blocks
-    N, d = 11_000_000, 28
-    xs = [torch.randn((N // G, d), dtype=torch.float64, device=dev) for _ in mine]
-    theta = torch.ones(d, dtype=torch.float64, device=dev) / np.sqrt(d)
-    ys = [(torch.rand(x.shape[0], dtype=torch.float64, device=dev) < torch.sigmoid(x @ theta)).to(torch.float64) for x in xs]
-    iters = 10
+    def cfg4():
+        # Newton LR 11M x 28, 8 row blocks
+        N, d = 11_000_000, 28
+        xs = [torch.randn((N // G, d), dtype=torch.float64, device=dev) for _ in mine]
+        theta = torch.ones(d, dtype=torch.float64, device=dev) / np.sqrt(d)
+        ys = [(torch.rand(x.shape[0], dtype=torch.float64, device=dev) < torch.sigmoid(x @ theta)).to(torch.float64) for x in xs]
+        iters = 10
 
-    def newton():
-        multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters, cc.lr_grad_hess_blocks, step=cc.newton_step)
-    t = timed(newton, 2 if quick else 3)
-    out["newton_lr_fused"] = {"value": t / iters, "unit": "s/iter",
-                              "workload": "Newton LR 11M x 28 float64, 8 row blocks over %d GPU(s), fused g|H kernel + one "
-                                          "all-reduce of 812 doubles per iteration" % world,
-                              "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters) / 1e9}
-    del xs, ys
-    torch.cuda.empty_cache()
+        def newton():
+            multi_gpu.newton_lr(system, comm, xs, ys, d, 0.0, iters, cc.lr_grad_hess_blocks, step=cc.newton_step)
+        t = timed(newton, 2 if quick else 3)
+        out["newton_lr_fused"] = {"value": t / iters, "unit": "s/iter",
+                                  "workload": "Newton LR 11M x 28 float64, 8 row blocks over %d GPU(s), fused g|H kernel + one "
+                                              "all-reduce of 812 doubles per iteration" % world,
+                                  "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters) / 1e9}
+
+    _guarded(out, "bop_add", cfg1)
+    _guarded(out, "tsqr_r", cfg3)
+    _guarded(out, "newton_lr_fused", cfg4)
     return out
 
 
-def api_workloads(host, quick):
+def api_workloads(host, quick, out=None):
     """cfg1 / cfg3 / cfg4 at N > 1 THROUGH THE PLUGIN API: the reference's BlockArray operators,
     ArrayApplication.indirect_tsr and glms.newton over SpmdSystem, blocks living on their owners.  Whole-job figures,
     device-timed, max over ranks (same conventions as sharded_workloads, which calls the drivers directly)."""
@@ -544,7 +570,8 @@ def api_workloads(host, quick):
     system, app = host.system, host.app
     world, rank = system.world_size, system.rank
     dev = torch.device("cuda", torch.cuda.current_device())
-    out = {}
+    out = {} if out is None else out
+    G = 8
 
     def timed(fn, iters):
         fn()
@@ -566,54 +593,60 @@ def api_workloads(host, quick):
             ba.blocks[entry].oid = system.put_at(fill(bshape) if mine else None, entry, gshape, shape=bshape, dtype=np.float64)
         return ba
 
-    n, G = 100_000_000, 8
-    U = distributed((n,), (n // G,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
-    V = distributed((n,), (n // G,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
-    t = timed(lambda: (host.launch(U + V), torch.cuda.synchronize()), 5 if quick else 20)
-    out["bop_add_api"] = {"value": 24.0 * n / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
-                          "workload": "BlockArray.__add__ of two 1e8-element float64 arrays, 8 blocks over %d GPU(s) through "
-                                      "SpmdSystem (shard-local, no exchange)" % world}
-    del U, V
+    def cfg1():
+        n = 100_000_000
+        U = distributed((n,), (n // G,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
+        V = distributed((n,), (n // G,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
+        t = timed(lambda: (host.launch(U + V), torch.cuda.synchronize()), 5 if quick else 20)
+        out["bop_add_api"] = {"value": 24.0 * n / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
+                              "workload": "BlockArray.__add__ of two 1e8-element float64 arrays, 8 blocks over %d GPU(s) through "
+                                          "SpmdSystem (shard-local, no exchange)" % world}
 
-    m, ncol = 16_777_216, 128
-    X = distributed((m, ncol), (m // G, ncol), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
-    flops_r = 2.0 * m * ncol ** 2 - 2.0 * ncol ** 3 / 3.0
-    t = timed(lambda: (host.launch(app.indirect_tsr(X)), torch.cuda.synchronize()), 2 if quick else 3)
-    out["tsqr_r_api"] = {"value": flops_r / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
-                         "workload": "ArrayApplication.indirect_tsr on 16777216 x 128 float64, 8 row blocks over %d GPU(s): local R "
-                                     "per block, stacked-R qr as a binary tree over the ranks, R replicated" % world}
-    del X
-    torch.cuda.empty_cache()
+    def cfg3():
+        m, ncol = 16_777_216, 128
+        X = distributed((m, ncol), (m // G, ncol), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
+        flops_r = 2.0 * m * ncol ** 2 - 2.0 * ncol ** 3 / 3.0
+        t = timed(lambda: (host.launch(app.indirect_tsr(X)), torch.cuda.synchronize()), 2 if quick else 3)
+        out["tsqr_r_api"] = {"value": flops_r / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
+                             "workload": "ArrayApplication.indirect_tsr on 16777216 x 128 float64, 8 row blocks over %d GPU(s): "
+                                         "per-block Gram matrices summed on their owners, one all-reduce, one factorization "
+                                         "(Householder tree over the ranks when the condition bound refuses), R replicated" % world}
 
-    N, d = 11_000_000, 28
-    X = distributed((N, d), (N // G, d), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
-    y = distributed((N,), (N // G,), lambda s: (torch.rand(s, dtype=torch.float64, device=dev) < 0.5).to(torch.float64))
-    model = host.logistic_model()
-    iters = 2 if quick else 4
-    t = timed(lambda: (host.launch(host.newton(model, X, y, 1e-300, iters)), torch.cuda.synchronize()), 1 if quick else 2)
-    out["newton_lr_interface_path"] = {
-        "value": t / iters, "unit": "s/iter",
-        "workload": "glms.newton on 11M x 28 float64, 8 row blocks over %d GPU(s) through SpmdSystem: ~15 kernel calls per block "
-                    "per iteration on the block's owner, g and H all-reduced, beta replicated" % world,
-        "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters) / 1e9}
-    from nums_b200 import glms_fused
-    iters_fused = 10
+    def cfg4():
+        N, d = 11_000_000, 28
+        X = distributed((N, d), (N // G, d), lambda s: torch.randn(s, dtype=torch.float64, device=dev))
+        y = distributed((N,), (N // G,), lambda s: (torch.rand(s, dtype=torch.float64, device=dev) < 0.5).to(torch.float64))
+        model = host.logistic_model()
+        iters = 2 if quick else 4
+        t = timed(lambda: (host.launch(host.newton(model, X, y, 1e-300, iters)), torch.cuda.synchronize()), 1 if quick else 2)
+        out["newton_lr_interface_path"] = {
+            "value": t / iters, "unit": "s/iter",
+            "workload": "glms.newton on 11M x 28 float64, 8 row blocks over %d GPU(s) through SpmdSystem: ~15 kernel calls per block "
+                        "per iteration on the block's owner, g and H all-reduced, beta replicated" % world,
+            "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters) / 1e9}
+        from nums_b200 import glms_fused
+        iters_fused = 10
 
-    def fused_glms():
-        beta0 = app.zeros((d,), (d,), np.float64)
-        host.launch(glms_fused.newton(app, model, beta0, X, y, app.scalar(0.0), iters_fused))
-        torch.cuda.synchronize()
-    t = timed(fused_glms, 2 if quick else 3)
-    out["newton_lr_fused_glms"] = {
-        "value": t / iters_fused, "unit": "s/iter",
-        "workload": "nums_b200.glms_fused.newton through SpmdSystem on %d GPU(s): lr_grad_hess per block on its owner, g | H "
-                    "summed locally and all-reduced (one 812-double NCCL all-reduce per iteration), newton_step replicated, "
-                    "status read one iteration late; 11M x 28 float64, 8 row blocks, 10 iterations" % world,
-        "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_fused) / 1e9}
-    del X, y
-    torch.cuda.empty_cache()
-    if world >= 8 and not quick:
+        def fused_glms():
+            beta0 = app.zeros((d,), (d,), np.float64)
+            host.launch(glms_fused.newton(app, model, beta0, X, y, app.scalar(0.0), iters_fused))
+            torch.cuda.synchronize()
+        t = timed(fused_glms, 2 if quick else 3)
+        out["newton_lr_fused_glms"] = {
+            "value": t / iters_fused, "unit": "s/iter",
+            "workload": "nums_b200.glms_fused.newton through SpmdSystem on %d GPU(s): lr_grad_hess per block on its owner, g | H "
+                        "summed locally and all-reduced (one 812-double NCCL all-reduce per iteration), newton_step replicated, "
+                        "status read one iteration late; 11M x 28 float64, 8 row blocks, 10 iterations" % world,
+            "algorithmic_GBps": 8.0 * N * (d + 1) / (t / iters_fused) / 1e9}
+
+    def cfg5():
         out["large_matmul_65536"] = large_matmul_workload(host, steps=2)
+
+    _guarded(out, "bop_add_api", cfg1)
+    _guarded(out, "tsqr_r_api", cfg3)
+    _guarded(out, "newton_lr_api", cfg4)
+    if world >= 8 and not quick:
+        _guarded(out, "large_matmul_65536", cfg5)
     return out
 
 
@@ -1029,6 +1062,63 @@ def run_gpu(args):
         summa.run(packed)              # collective: every rank takes part in the verification pass
     sync_all()
 
+    # ---- everything the headline needs is measured: from here on a watchdog guarantees the JSON line ----------
+    # The secondary workloads are collective at N > 1; should one of them fail or stall on some rank, rank 0
+    # still prints the headline (with the failure recorded under "workloads") and every rank exits.
+    bytes_matrix = 8 * N_MATMUL * N_MATMUL
+    clocks = None
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(t_mark0, t_mark1)
+    state = {"workloads": None, "roofline": None, "cpu_baseline": None, "done": False}
+
+    def compose():
+        return {
+            "metric": "blocked_matmul_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "blocked matmul float64 16384x16384 @ 16384x16384, 8x8 grid of 2048x2048 blocks "
+                                   "(BASELINE.json configs[1])",
+                       "parallelism": parallelism,
+                       "parity_rel_err": verified,
+                       "l2_policy": "inputs (2 x 2.1 GB) and output (2.1 GB) exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": e2e_value, "unit": "TFLOP/s",
+                    "h2d_bytes_per_step": 2 * bytes_matrix, "d2h_bytes_per_step": bytes_matrix, "steps": e2e_steps,
+                    "what": ("pinned host blocks -> system.put (async, upload stream) -> A @ B through the block kernel interface "
+                             "(deferred, launched in groups as operands land) -> CudaSystem.get_assembled on the host (block rows "
+                             "drained on a download stream); wall clock, host<->device copies inside") if world == 1 else
+                            ("every rank: pinned host blocks it owns -> put_at (async upload) -> BlockArray.__matmul__ over SpmdSystem "
+                             "(exchange + grouped launch) -> get_owned: the C blocks it owns back to its host; wall clock, "
+                             "host<->device copies inside, max over ranks") if api_path else
+                            "every rank: put of its blocks -> SummaMatmul driver -> get of its C blocks; wall clock, max over ranks",
+                    "through_reference_BlockArray_get": e2e_blockarray_get},
+            "gpu_launches": int(launches),
+            "parity_check": {"what": "one 2048x2048 block of C vs NumPy on the host (relative Frobenius error)",
+                             "rel_err": verified, "bar": 1e-10},
+            "clocks": clocks,
+            "roofline": state["roofline"],
+            "cpu_baseline": state["cpu_baseline"],
+            "workloads": state["workloads"],
+        }
+
+    def watchdog_fired():
+        if state["done"]:
+            return
+        state["done"] = True
+        if rank == 0:
+            note = {"error": "secondary workloads did not finish within %d s; headline figures above are complete" % args.watchdog}
+            if isinstance(state["workloads"], dict):
+                state["workloads"]["_watchdog"] = note
+            else:
+                state["workloads"] = note
+            emit(compose())
+        else:
+            time.sleep(2.0)
+        os._exit(0)
+    watchdog = threading.Timer(float(args.watchdog), watchdog_fired)
+    watchdog.daemon = True
+    watchdog.start()
+
     sharded = None
     if world > 1 and not args.skip_workloads:
         packed = None
@@ -1036,22 +1126,21 @@ def run_gpu(args):
             del A, B
         torch.cuda.empty_cache()
         raw_system = system.local if api_path else system
-        sharded = sharded_workloads(raw_system, comm, quick=args.quick)   # collective: all ranks
+        state["workloads"] = sharded = {}
+        sharded.update(sharded_workloads(raw_system, comm, quick=args.quick))   # collective: all ranks
         if api_path:
-            sharded.update(api_workloads(host, quick=args.quick))
+            api_workloads(host, quick=args.quick, out=sharded)
 
     if rank != 0:
+        state["done"] = True
+        watchdog.cancel()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
 
     # ---- rank 0, N == 1 extras: roofline of the dominant kernel, CPU baseline, other workloads ----------------
-    sampler.stop()
-    clocks = sampler.summary(t_mark0, t_mark1)
     roofline = None
-    cpu_baseline = None
-    workloads = None
     if world == 1:
         # Dominant kernel: the grouped DMMA launch that a step's dot/add chain collapses into
         # (one launch per step, see nums_b200/deferred.py).  Event-timed here, in isolation.
@@ -1101,14 +1190,18 @@ def run_gpu(args):
                 roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             pass
+        state["roofline"] = roofline
         del A, B
         torch.cuda.empty_cache()
         if not args.skip_cpu:
-            cpu_baseline = measure_cpu(a_host, b_host)
+            try:
+                state["cpu_baseline"] = measure_cpu(a_host, b_host)
+            except Exception as exc:  # noqa: BLE001 -- reported, the headline stands
+                state["cpu_baseline"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         if not args.skip_workloads:
-            workloads = other_workloads(host, quick=args.quick)
+            state["workloads"] = {}
+            other_workloads(host, quick=args.quick, out=state["workloads"])
     else:
-        workloads = sharded
         try:    # per-GPU rate of the whole product (both grouped launches + whatever transfer time is exposed)
             sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
             peak = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * (256 / 16.0) * 2 * sm_mhz * 1e6 / 1e12
@@ -1127,39 +1220,16 @@ def run_gpu(args):
             peaks = json.load(f)
     except Exception:  # noqa: BLE001
         pass
-    if workloads and peaks.get("hbm_gbs"):
-        for key in ("bop_add", "bop_mul"):
-            if key in workloads:
+    workloads = state["workloads"]
+    if isinstance(workloads, dict) and peaks.get("hbm_gbs"):
+        for key in ("bop_add", "bop_mul", "bop_add_api"):
+            if key in workloads and "value" in workloads[key]:
                 workloads[key]["frac_of_measured_hbm"] = workloads[key]["value"] / (peaks["hbm_gbs"] * world)
 
-    line = {
-        "metric": "blocked_matmul_fp64_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "blocked matmul float64 16384x16384 @ 16384x16384, 8x8 grid of 2048x2048 blocks "
-                               "(BASELINE.json configs[1])",
-                   "parallelism": parallelism,
-                   "parity_rel_err": verified,
-                   "l2_policy": "inputs (2 x 2.1 GB) and output (2.1 GB) exceed the 126 MB L2; no flush needed"},
-        "e2e": {"value": e2e_value, "unit": "TFLOP/s",
-                "h2d_bytes_per_step": 2 * bytes_matrix, "d2h_bytes_per_step": bytes_matrix, "steps": e2e_steps,
-                "what": ("pinned host blocks -> system.put (async, upload stream) -> A @ B through the block kernel interface "
-                         "(deferred, launched in groups as operands land) -> CudaSystem.get_assembled on the host (block rows "
-                         "drained on a download stream); wall clock, host<->device copies inside") if world == 1 else
-                        ("every rank: pinned host blocks it owns -> put_at (async upload) -> BlockArray.__matmul__ over SpmdSystem "
-                         "(exchange + grouped launch) -> get_owned: the C blocks it owns back to its host; wall clock, "
-                         "host<->device copies inside, max over ranks") if api_path else
-                        "every rank: put of its blocks -> SummaMatmul driver -> get of its C blocks; wall clock, max over ranks",
-                "through_reference_BlockArray_get": e2e_blockarray_get},
-        "gpu_launches": int(launches),
-        "parity_check": {"what": "one 2048x2048 block of C vs NumPy on the host (relative Frobenius error)",
-                         "rel_err": verified, "bar": 1e-10},
-        "clocks": clocks,
-        "roofline": roofline,
-        "cpu_baseline": cpu_baseline,
-        "workloads": workloads,
-    }
-    emit(line)
+    state["roofline"] = roofline
+    state["done"] = True
+    watchdog.cancel()
+    emit(compose())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -1183,6 +1253,8 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-workloads", action="store_true", help="only the headline matmul")
     ap.add_argument("--quick", action="store_true", help="fewer repetitions of the secondary workloads")
+    ap.add_argument("--watchdog", type=int, default=900,
+                    help="seconds the secondary workloads may take before the headline line is printed without them")
     ap.add_argument("--large", action="store_true", help="config 5 instead: 65536^2 matmul (one-off record run)")
     ap.add_argument("--summa-driver", action="store_true",
                     help="N > 1: the hand-called SummaMatmul driver (round 1) instead of BlockArray.__matmul__ over SpmdSystem")

@@ -622,6 +622,48 @@ splitk_fold_kernel(const double* __restrict__ partial, int splits, int64_t M, in
   }
 }
 
+// The same fold for MANY partials of a SMALL result (per-CTA partials of the streaming kernels: up to
+// one per SM for a 28 x 28 output): one warp per output element, lane l adds partials l, l + 32, ...
+// (four independent loads in flight), then a fixed-order butterfly -- deterministic, and ~3 us where
+// the one-thread-per-element loop above spends `splits` dependent L2 round trips (20 us at 148).
+__global__ void __launch_bounds__(256)
+fold_partials_warp_kernel(const double* __restrict__ partial, int splits, int64_t M, int64_t N,
+                          const double* __restrict__ cin, int64_t ldcin, double* __restrict__ out, int64_t ldc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = M * N;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= total) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int s = lane;
+  for (; s + 96 < splits; s += 128) {
+    a0 += partial[(int64_t)s * total + i];
+    a1 += partial[(int64_t)(s + 32) * total + i];
+    a2 += partial[(int64_t)(s + 64) * total + i];
+    a3 += partial[(int64_t)(s + 96) * total + i];
+  }
+  for (; s < splits; s += 32) a0 += partial[(int64_t)s * total + i];
+  double acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const int64_t m = i / N, n = i - m * N;
+    if (cin != nullptr) acc += cin[m * ldcin + n];
+    out[m * ldc + n] = acc;
+  }
+}
+
+inline int launch_fold_partials(const double* partial, int splits, int64_t M, int64_t N, const double* cin,
+                                int64_t ldcin, double* out, int64_t ldc, cudaStream_t s) {
+  if (splits >= 16 && M * N <= 4096) {
+    fold_partials_warp_kernel<<<(unsigned)ceil_div(M * N, 8), 256, 0, s>>>(partial, splits, M, N, cin, ldcin, out, ldc);
+  } else {
+    splitk_fold_kernel<<<blocks_for(M * N, 256, (int64_t)sm_count() * 8), 256, 0, s>>>(partial, splits, M, N, cin, ldcin,
+                                                                                       out, ldc);
+  }
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
 // ======================================================================================
 // Skinny A^T B: C[M,N] = A^T B with M, N <= 32 and a very long contraction (K rows)
 // ======================================================================================
@@ -752,10 +794,160 @@ int launch_skinny_rows(const double* A, int64_t lda, const double* B, int64_t ld
   dgemm_tn_skinny_kernel<MB, NB, kSkinnyRows><<<grid, 256, smem, s>>>(A, lda, B, ldb, M, N, K, same,
                                                                      static_cast<double*>(ws));
   NUMS_LAUNCH_OK();
-  splitk_fold_kernel<<<blocks_for((int64_t)M * N, 256), 256, 0, s>>>(static_cast<const double*>(ws), grid, M, N, Cin,
-                                                                     ldcin, C, ldc);
+  return launch_fold_partials(static_cast<const double*>(ws), grid, M, N, Cin, ldcin, C, ldc, s);
+}
+
+// --------------------------------------------------------------------------------------
+// Dense operands (lda == M, ldb == N): a chunk of 128 rows is ONE contiguous run of memory per operand,
+// so a producer warp fetches it with one bulk asynchronous copy each (cp.async.bulk -> UBLKCP, tracked by
+// the stage's `full` mbarrier) and the eight MMA warps free-run over the ring, handing stages back through
+// `empty` mbarriers -- no per-thread copy instructions, no CTA barrier per chunk (the cp.async version
+// above spends 32 copy instructions with 14 of 32 lanes active per warp and chunk, and measured 1.55 TB/s
+// on the 28 x n_b by n_b x 28 Hessian product of glms.hessian, glms.py:232-238).  Tiles keep the operand's
+// own pitch (M resp. N doubles): conflict free when the pitch is 4 or 12 (mod 16), e.g. 28; columns past
+// M / N in the last 8-wide block and rows past K in the last chunk are masked in registers.
+// --------------------------------------------------------------------------------------
+inline bool skinny_dense_enabled() {   // NUMS_SKINNY_DENSE=0 selects the cp.async ring (A/B measurements)
+  static const bool on = []() { const char* v = getenv("NUMS_SKINNY_DENSE"); return !(v && v[0] == '0'); }();
+  return on;
+}
+constexpr int kSkDenseRows = 128;
+constexpr int kSkDenseStages = 3;
+constexpr int kSkDenseThreads = 256 + 32;
+
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_addr_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr_u32(bar))
+               : "memory");
+}
+
+template <int MB, int NB>
+__global__ void __launch_bounds__(kSkDenseThreads, 1)
+dgemm_tn_skinny_dense_kernel(const double* __restrict__ A, const double* __restrict__ B, int M, int N, int64_t K,
+                             int same, double* __restrict__ partial) {
+  extern __shared__ __align__(128) double skd_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int stage_doubles = kSkDenseRows * (M + (same ? 0 : N));
+  double* ring = skd_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)kSkDenseStages * stage_doubles + 32);   // 32 doubles of slack:
+  uint64_t* empty = full + kSkDenseStages;                                    // masked fragment reads run past the last row
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSkDenseStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t nchunks = (K + kSkDenseRows - 1) / kSkDenseRows;
+  const int64_t my_chunks = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  double acc[MB][NB][2];
+#pragma unroll
+  for (int i = 0; i < MB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int64_t i = 0; i < my_chunks; ++i) {
+        const int slot = (int)(i % kSkDenseStages);
+        const int64_t round = i / kSkDenseStages;
+        if (round > 0) {
+          mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before async writes
+        }
+        const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * kSkDenseRows;
+        const int64_t rows = (K - r0 < kSkDenseRows) ? (K - r0) : kSkDenseRows;
+        const uint32_t bytes_a = (uint32_t)(rows * M * sizeof(double));
+        const uint32_t bytes_b = same ? 0u : (uint32_t)(rows * N * sizeof(double));
+        double* dst = ring + (size_t)slot * stage_doubles;
+        mbar_expect_tx(&full[slot], bytes_a + bytes_b);
+        bulk_copy_g2s(dst, A + r0 * M, bytes_a, &full[slot]);
+        if (!same) bulk_copy_g2s(dst + kSkDenseRows * M, B + r0 * N, bytes_b, &full[slot]);
+      }
+    }
+  } else {
+    constexpr int kWarpRows = kSkDenseRows / 8;
+    const bool a_edge = g < M - 8 * (MB - 1);     // lane's column exists in the last 8-wide block of A / B
+    const bool b_edge = g < N - 8 * (NB - 1);
+    for (int64_t i = 0; i < my_chunks; ++i) {
+      const int slot = (int)(i % kSkDenseStages);
+      mbar_wait(&full[slot], (uint32_t)((i / kSkDenseStages) & 1));
+      const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * kSkDenseRows;
+      const int rows = (int)((K - r0 < kSkDenseRows) ? (K - r0) : kSkDenseRows);
+      const double* a = ring + (size_t)slot * stage_doubles + (size_t)warp * kWarpRows * M;
+      const double* b = same ? a : ring + (size_t)slot * stage_doubles + kSkDenseRows * M + (size_t)warp * kWarpRows * N;
+      const int pb = same ? M : N;
+#pragma unroll
+      for (int q = 0; q < kWarpRows / 4; ++q) {
+        const bool row_ok = warp * kWarpRows + 4 * q + t < rows;
+        double af[MB], bf[NB];
+#pragma unroll
+        for (int ii = 0; ii < MB; ++ii) {
+          const double v = a[(4 * q + t) * M + 8 * ii + g];
+          af[ii] = (row_ok && (ii < MB - 1 || a_edge)) ? v : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const double v = b[(4 * q + t) * pb + 8 * j + g];
+          bf[j] = (row_ok && (j < NB - 1 || b_edge)) ? v : 0.0;
+        }
+#pragma unroll
+        for (int ii = 0; ii < MB; ++ii)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) dmma884(acc[ii][j], af[ii], bf[j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);
+    }
+  }
+  __syncthreads();
+  // CTA fold: 8 warps -> one (MB*8) x (NB*8) tile in shared memory, then the M x N corner goes out
+  constexpr int TM = MB * 8, TN = NB * 8;
+  double* red = skd_smem;   // 8 * TM * TN doubles <= 64 KB; launch_skinny_dense checks that the ring is larger
+  if (warp < 8) {
+    double* mine = red + warp * TM * TN;
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        mine[(8 * i + g) * TN + 8 * j + 2 * t] = acc[i][j][0];
+        mine[(8 * i + g) * TN + 8 * j + 2 * t + 1] = acc[i][j][1];
+      }
+  }
+  __syncthreads();
+  double* out = partial + (size_t)blockIdx.x * M * N;
+  for (int e = threadIdx.x; e < M * N; e += kSkDenseThreads) {
+    const int r = e / N, c = e - r * N;
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w * TM * TN + r * TN + c];
+    out[e] = v;
+  }
+}
+
+template <int MB, int NB>
+int launch_skinny_dense(const double* A, const double* B, int M, int N, int64_t K, const double* Cin, int64_t ldcin,
+                        double* C, int64_t ldc, void* ws, size_t ws_bytes, cudaStream_t s, bool* handled) {
+  const int same = (A == B && M == N) ? 1 : 0;
+  const size_t ring_bytes = (size_t)kSkDenseStages * kSkDenseRows * (M + (same ? 0 : N)) * sizeof(double);
+  const size_t smem = ring_bytes + 32 * sizeof(double) + 2 * kSkDenseStages * sizeof(uint64_t);
+  *handled = false;
+  if (smem > 227 * 1024 || ring_bytes < (size_t)8 * (MB * 8) * (NB * 8) * sizeof(double)) return NUMS_OK;
+  *handled = true;
+  const int64_t nchunks = (K + kSkDenseRows - 1) / kSkDenseRows;
+  int grid = sm_count();
+  if (grid > nchunks) grid = (int)nchunks;
+  NUMS_NEED_WS((size_t)grid * M * N * sizeof(double), ws_bytes);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(dgemm_tn_skinny_dense_kernel<MB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  dgemm_tn_skinny_dense_kernel<MB, NB><<<grid, kSkDenseThreads, smem, s>>>(A, B, M, N, K, same, static_cast<double*>(ws));
   NUMS_LAUNCH_OK();
-  return NUMS_OK;
+  return launch_fold_partials(static_cast<const double*>(ws), grid, M, N, Cin, ldcin, C, ldc, s);
 }
 
 template <int MB, int NB>
@@ -763,6 +955,11 @@ int launch_skinny(const double* A, int64_t lda, const double* B, int64_t ldb, in
                   const double* Cin, int64_t ldcin, double* C, int64_t ldc, void* ws, size_t ws_bytes,
                   cudaStream_t s) {
   const bool same = (A == B && lda == ldb && M == N);
+  if (lda == M && ldb == N && skinny_dense_enabled()) {
+    bool handled = false;
+    const int rc = launch_skinny_dense<MB, NB>(A, B, M, N, K, Cin, ldcin, C, ldc, ws, ws_bytes, s, &handled);
+    if (rc != NUMS_OK || handled) return rc;
+  }
   constexpr int PA = skinny_pitch(MB * 8), PB = skinny_pitch(NB * 8);
   const size_t big = (size_t)kSkinnyStages * 256 * (PA + (same ? 0 : PB)) * sizeof(double);
   if (big <= 224 * 1024)
@@ -907,6 +1104,79 @@ gemv_narrow_rows_kernel(const T* __restrict__ A, int64_t rows, int cols, const T
   }
 }
 
+// float64, even cols <= 32, 16-byte aligned dense A: a warp owns 32 consecutive rows = one contiguous run of
+// 16 * cols 16-byte pieces; lane l loads pieces l, l + 32, ... (all HALF = cols / 2 loads independent and
+// coalesced), multiplies each by the matching pair of x (held in registers: a 32-row run starts on a row
+// boundary, so the pair a lane needs for its k-th piece never changes), parks the products in a per-warp
+// scratch and lane l adds the HALF products of row l in order.  No CTA barrier, no integer division in the
+// loop; the staged version above measured 2.8 TB/s on the LR forward pass X beta (cols = 28).
+template <int HALF>
+__global__ void __launch_bounds__(256, 2)
+gemv_rows_f64_narrow_kernel(const double* __restrict__ A, int64_t rows, const double* __restrict__ x, int64_t incx,
+                            const double* __restrict__ yin, double* __restrict__ y, int64_t incy) {
+  constexpr int COLS = 2 * HALF, PITCH = HALF + 1;
+  __shared__ double scratch[8][32 * PITCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sc = scratch[warp];
+  double2 xv[HALF];
+#pragma unroll
+  for (int k = 0; k < HALF; ++k) {
+    const int p = lane + 32 * k, c = p % HALF;
+    xv[k] = make_double2(x[(int64_t)(2 * c) * incx], x[(int64_t)(2 * c + 1) * incx]);
+  }
+  const int64_t chunks = (rows + 31) / 32;
+  const int64_t step = (int64_t)gridDim.x * 8;
+  for (int64_t ch = (int64_t)blockIdx.x * 8 + warp; ch < chunks; ch += step) {
+    const int64_t r0 = ch * 32;
+    const int left = (int)((rows - r0 < 32) ? rows - r0 : 32);
+    const double2* src = reinterpret_cast<const double2*>(A + r0 * COLS);
+    double2 v[HALF];
+    if (left == 32) {
+#pragma unroll
+      for (int k = 0; k < HALF; ++k) v[k] = __ldcs(src + lane + 32 * k);
+    } else {
+#pragma unroll
+      for (int k = 0; k < HALF; ++k) v[k] = (lane + 32 * k < left * HALF) ? __ldcs(src + lane + 32 * k) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < HALF; ++k) {
+      const int p = lane + 32 * k;          // piece p = column pair p % HALF of row p / HALF (constant divisor)
+      sc[p + p / HALF] = fma(v[k].y, xv[k].y, v[k].x * xv[k].x);      // == (p / HALF) * PITCH + p % HALF
+    }
+    __syncwarp();
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < HALF; ++c) acc += sc[lane * PITCH + c];
+    __syncwarp();
+    if (lane < left) {
+      const int64_t r = r0 + lane;
+      y[r * incy] = yin ? acc + yin[r * incy] : acc;
+    }
+  }
+}
+
+template <int HALF>
+int launch_gemv_rows_f64_narrow(const double* A, int64_t rows, const double* x, int64_t incx, const double* yin,
+                                double* y, int64_t incy, cudaStream_t s) {
+  const unsigned grid = blocks_for((rows + 31) / 32, 8, (int64_t)sm_count() * 6);
+  gemv_rows_f64_narrow_kernel<HALF><<<grid, 256, 0, s>>>(A, rows, x, incx, yin, y, incy);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
+inline int run_gemv_rows_f64_narrow(const double* A, int64_t rows, int cols, const double* x, int64_t incx,
+                                    const double* yin, double* y, int64_t incy, cudaStream_t s) {
+  switch (cols / 2) {
+#define NUMS_GEMV_NARROW(H) case H: return launch_gemv_rows_f64_narrow<H>(A, rows, x, incx, yin, y, incy, s)
+    NUMS_GEMV_NARROW(1); NUMS_GEMV_NARROW(2); NUMS_GEMV_NARROW(3); NUMS_GEMV_NARROW(4);
+    NUMS_GEMV_NARROW(5); NUMS_GEMV_NARROW(6); NUMS_GEMV_NARROW(7); NUMS_GEMV_NARROW(8);
+    NUMS_GEMV_NARROW(9); NUMS_GEMV_NARROW(10); NUMS_GEMV_NARROW(11); NUMS_GEMV_NARROW(12);
+    NUMS_GEMV_NARROW(13); NUMS_GEMV_NARROW(14); NUMS_GEMV_NARROW(15); NUMS_GEMV_NARROW(16);
+#undef NUMS_GEMV_NARROW
+  }
+  NUMS_FAIL(NUMS_ERR_INVALID, "gemv: narrow kernel does not serve %d columns", cols);
+}
+
 // Partial y[c] = sum_{r in segment} A[r, c] w[r] for a dense row-major A with few columns
 // (cols <= 256): flat coalesced sweep, thread t always sees column t % cols.
 // grid.x = segments; partial layout (segment, cols).
@@ -953,16 +1223,30 @@ gemv_t_wide_kernel(const T* __restrict__ A, int64_t lda, int64_t rows, int64_t c
   partial[(int64_t)blockIdx.y * cols + c] = acc0 + acc1;
 }
 
-// y[c] = (yin ? yin[c] : 0) + sum_s partial[s][c]
+// y[c] = (yin ? yin[c] : 0) + sum_s partial[s][c]: one warp per column, lane l adds segments l, l + 32, ...
+// (four independent loads in flight) and a fixed-order butterfly finishes -- deterministic.  (One thread per
+// column walking all segments was a chain of `segs` dependent L2 round trips: 54 us for the 1184 partials
+// of the LR gradient X^T (mu - y), more than the 57 us sweep over X that produced them.)
 template <typename T>
 __global__ void __launch_bounds__(256)
 fold_vector_kernel(const T* __restrict__ partial, int64_t segs, int64_t cols, const T* __restrict__ yin,
                    T* __restrict__ y, int64_t incy) {
-  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= cols) return;
-  T acc = T(0);
-  for (int64_t s = 0; s < segs; ++s) acc += partial[s * cols + c];
-  y[c * incy] = yin ? acc + yin[c * incy] : acc;
+  T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+  int64_t s = lane;
+  for (; s + 96 < segs; s += 128) {
+    a0 += partial[s * cols + c];
+    a1 += partial[(s + 32) * cols + c];
+    a2 += partial[(s + 64) * cols + c];
+    a3 += partial[(s + 96) * cols + c];
+  }
+  for (; s < segs; s += 32) a0 += partial[s * cols + c];
+  T acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[c * incy] = yin ? acc + yin[c * incy] : acc;
 }
 
 // Dot product partials: partial[b] = sum over the block's segment of x[i] * y[i].
@@ -997,6 +1281,11 @@ dot_partial_kernel(const T* __restrict__ x, int64_t incx, const T* __restrict__ 
 template <typename T>
 int run_gemv_rows(const T* A, int64_t lda, int64_t rows, int64_t cols, const T* x, int64_t incx,
                   const T* yin, T* y, int64_t incy, cudaStream_t s) {
+  if constexpr (std::is_same<T, double>::value) {
+    if (cols >= 2 && cols <= 32 && cols % 2 == 0 && lda == cols && rows >= 4096
+        && (reinterpret_cast<uintptr_t>(A) & 15u) == 0)
+      return run_gemv_rows_f64_narrow(A, rows, (int)cols, x, incx, yin, y, incy, s);
+  }
   if (cols <= 64 && lda == cols) {
     const int pitch = (int)cols | 1;
     const size_t smem = (size_t)(256 * pitch + cols) * sizeof(T);
@@ -1030,7 +1319,7 @@ int run_gemv_t(const T* A, int64_t lda, int64_t rows, int64_t cols, const T* w, 
     T* partial = static_cast<T*>(ws);
     gemv_t_narrow_kernel<T><<<(unsigned)segs, 256, 0, s>>>(A, rows, (int)cols, w, incw, rows_per_seg, partial);
     NUMS_LAUNCH_OK();
-    fold_vector_kernel<T><<<(unsigned)ceil_div(cols, 256), 256, 0, s>>>(partial, segs, cols, yin, y, incy);
+    fold_vector_kernel<T><<<(unsigned)ceil_div(cols, 8), 256, 0, s>>>(partial, segs, cols, yin, y, incy);
     NUMS_LAUNCH_OK();
     return NUMS_OK;
   }
@@ -1047,7 +1336,7 @@ int run_gemv_t(const T* A, int64_t lda, int64_t rows, int64_t cols, const T* w, 
   dim3 grid((unsigned)col_tiles, (unsigned)segs);
   gemv_t_wide_kernel<T><<<grid, 256, 0, s>>>(A, lda, rows, cols, w, incw, rows_per_seg, partial);
   NUMS_LAUNCH_OK();
-  fold_vector_kernel<T><<<(unsigned)col_tiles, 256, 0, s>>>(partial, segs, cols, yin, y, incy);
+  fold_vector_kernel<T><<<(unsigned)ceil_div(cols, 8), 256, 0, s>>>(partial, segs, cols, yin, y, incy);
   NUMS_LAUNCH_OK();
   return NUMS_OK;
 }

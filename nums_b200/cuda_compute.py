@@ -38,9 +38,29 @@ _SHORT_OP_NAMES = {
     "eq": "equal", "ne": "not_equal", "divide": "true_divide", "mod": "remainder",
 }
 
-# Whether inv/cholesky read back the pivot status (one 4-byte D2H sync) to raise LinAlgError
-# like NumPy does.  On by default: same error behaviour as the reference.
-CHECK_FACTORIZATION_STATUS = True
+# How inv / cholesky report a singular / non-positive-definite block (np.linalg.LinAlgError in the reference):
+#   "deferred" (default) -- the kernel's status word stays on the device and is examined at the next point where
+#       the host waits for the device anyway (get / touch / synchronize): the error surfaces there, the way a
+#       failed remote task of the reference's Ray systems surfaces at ray.get, and a loop such as glms.newton
+#       (one inv per iteration, glms.py:368) keeps the host running ahead of the GPU;
+#   "eager" -- a 4-byte read-back (one stream synchronisation) inside the call, raising from the call itself
+#       exactly where NumPy would (NUMS_FACTORIZATION_STATUS=eager);
+#   "off"   -- never checked.
+CHECK_FACTORIZATION_STATUS = __import__("os").environ.get("NUMS_FACTORIZATION_STATUS", "deferred")
+_PENDING_STATUS = []          # [(int32 device scalar, message)] of factorizations not yet examined
+_PENDING_STATUS_MAX = 64
+
+
+def check_pending_status():
+    """Examine the status words of every factorization launched since the last check (the caller has
+    synchronised, or is about to: each read is a 4-byte copy).  Raises LinAlgError for the first failure."""
+    if not _PENDING_STATUS:
+        return
+    pending = list(_PENDING_STATUS)
+    del _PENDING_STATUS[:]
+    for info, message in pending:
+        if int(info.cpu().item()) != 0:
+            raise np.linalg.LinAlgError(message)
 
 
 class RNG(_RNGInterface):
@@ -77,7 +97,7 @@ def _device():
     """torch.device of this process' GPU (one process drives one GPU; cached per current device index --
     this sits on the per-block dispatch path)."""
     try:
-        index = torch.cuda.current_device()
+        index = _raw_current_device() if (_DEVICES and _raw_current_device is not None) else torch.cuda.current_device()    # (the first call initialises CUDA)
     except Exception:  # noqa: BLE001 -- no driver / no device
         index = None
     dev = _DEVICES.get(index)
@@ -130,11 +150,30 @@ def await_uploads(stream=None, upto=None):
         _Transfers.awaited[key] = seq
 
 
+# Raw handle of the current stream without building a torch.cuda.Stream object (that constructor was the
+# largest single item of the per-kernel dispatch cost: ~8 us of ~45); the private accessor is the one
+# torch.cuda.current_stream itself is built on, with the public API as the fallback.
+try:
+    _raw_current_stream = torch._C._cuda_getCurrentRawStream
+    _raw_current_device = torch._C._cuda_getDevice
+except AttributeError:  # pragma: no cover
+    _raw_current_stream = _raw_current_device = None
+
+
 def _stream_unordered():
+    if _raw_current_stream is not None:
+        return _raw_current_stream(_raw_current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
 def _stream():
+    """Handle of the current stream, ordered after every upload issued so far (see _Transfers)."""
+    if _raw_current_stream is not None:
+        key = _raw_current_stream(_raw_current_device())
+        if _Transfers.seq and _Transfers.awaited.get(key, 0) < _Transfers.seq:
+            torch.cuda.current_stream().wait_event(_Transfers.last_event)
+            _Transfers.awaited[key] = _Transfers.seq
+        return key
     cur = torch.cuda.current_stream()
     key = cur.cuda_stream
     if _Transfers.seq and _Transfers.awaited.get(key, 0) < _Transfers.seq:
@@ -232,6 +271,7 @@ def download(t):
     """Device tensor -> numpy array (synchronises the current stream)."""
     if isinstance(t, Touched):
         torch.cuda.current_stream().synchronize()
+        check_pending_status()
         return t.ok
     if not isinstance(t, torch.Tensor):
         return t
@@ -239,9 +279,12 @@ def download(t):
         if not t.is_contiguous():
             t = _materialize(t)
         await_uploads()
-        return t.cpu().numpy()
+        out = t.cpu().numpy()
+        check_pending_status()
+        return out
     host = _to_pinned(t)
     torch.cuda.current_stream().synchronize()
+    check_pending_status()
     return host.numpy()
 
 
@@ -250,6 +293,7 @@ def download_many(tensors):
     staged = [(_to_pinned(t) if isinstance(t, torch.Tensor) and t.numel() * t.element_size() >= (1 << 16) else None)
               for t in tensors]
     torch.cuda.current_stream().synchronize()
+    check_pending_status()
     return [h.numpy() if h is not None else download(t) for h, t in zip(staged, tensors)]
 
 
@@ -1105,12 +1149,21 @@ def _single_cta_factor(fn, arr, message):
         arr = _materialize(arr)
     n = arr.shape[0]
     out = _empty((n, n), _lib.numpy_dtype(arr.dtype))
-    info = _empty((), np.int32) if CHECK_FACTORIZATION_STATUS else None
+    mode = CHECK_FACTORIZATION_STATUS
+    if mode is True:
+        mode = "eager"
+    info = _empty((), np.int32) if mode and mode != "off" else None
     LIB.call_ws(fn, arr.device,
                 ((_lib.dtype_code(arr.dtype), n, arr.data_ptr(), n, out.data_ptr(), n,
                   info.data_ptr() if info is not None else None), (_stream(),)))
-    if info is not None and int(info.cpu().item()) != 0:
-        raise np.linalg.LinAlgError(message)
+    if info is not None:
+        if mode == "eager":
+            if int(info.cpu().item()) != 0:
+                raise np.linalg.LinAlgError(message)
+        else:
+            _PENDING_STATUS.append((info, message))
+            if len(_PENDING_STATUS) > _PENDING_STATUS_MAX:
+                check_pending_status()
     return out
 
 

@@ -116,6 +116,7 @@ class CudaSystem(object):
                 return cuda_compute.download_many(object_ids)
             if object_ids and all(isinstance(o, cuda_compute.Touched) for o in object_ids):
                 torch.cuda.current_stream().synchronize()     # one wait for a whole BlockArray.touch()
+                cuda_compute.check_pending_status()
                 return [o.ok for o in object_ids]
             return [self.get(o) for o in object_ids]
         if isinstance(object_ids, tuple):
@@ -135,6 +136,7 @@ class CudaSystem(object):
 
         def wait():
             done.synchronize()
+            cuda_compute.check_pending_status()
             return host.numpy()
         return wait
 
@@ -294,3 +296,4 @@ class CudaSystem(object):
     def synchronize(self):
         self.contractions.flush()
         torch.cuda.current_stream().synchronize()
+        cuda_compute.check_pending_status()

@@ -487,6 +487,30 @@ def test_tensordot_vector_forms(cuda_system, oracle):
         _tdot(cuda_system, oracle, u, v)
 
 
+@pytest.mark.parametrize("k", [8192, 8192 + 127, 100001, 1 << 20])
+def test_tensordot_skinny_dense_and_narrow_gemv(cuda_system, oracle, k):
+    """The streaming kernels behind the unfused LR step (glms.py:222-238): A^T B with M, N <= 32 over a long
+    contraction (bulk-copy ring, dgemm_tn_skinny_dense_kernel), A x for a narrow dense A (gemv_rows_f64_narrow_kernel)
+    and A^T w (gemv_t_narrow_kernel + the warp-parallel fold); every even width, ragged last chunks, A^T A."""
+    rng = np.random.default_rng(k)
+    widths = [(28, 28), (30, 2), (2, 32), (32, 32), (16, 24), (12, 20), (4, 6), (26, 18)] if k <= 100001 else [(28, 28), (6, 32)]
+    for m, n in widths:
+        A = rng.standard_normal((k, m))
+        B = rng.standard_normal((k, n))
+        _tdot(cuda_system, oracle, A, B, a_T=True)
+        t = cuda_system.put(A)                                              # X^T X on ONE block: the operand is loaded once
+        gram = cuda_system.get(cuda_system.bop("tensordot", t, t, (m, k), (k, m), True, False, axes=1, syskwargs={}))
+        assert rel_fro(gram, A.T @ A) <= GEMM_TOL
+    for cols in ([2, 4, 6, 10, 14, 16, 22, 26, 28, 30, 32] if k <= 100001 else [28]):
+        A = rng.standard_normal((k, cols))
+        x = rng.standard_normal(cols)
+        w = rng.standard_normal(k)
+        _tdot(cuda_system, oracle, A, x)
+        _tdot(cuda_system, oracle, A, w, a_T=True)
+    u, v = rng.standard_normal(k), rng.standard_normal(k)
+    _tdot(cuda_system, oracle, u, v)
+
+
 def test_tensordot_int_f32_nd(cuda_system, oracle):
     A = np.arange(6 * 7, dtype=np.int64).reshape(6, 7)       # test_bop.py:38-42 uses arange matrices
     B = np.arange(7 * 5, dtype=np.int64).reshape(7, 5)
@@ -600,7 +624,20 @@ def test_inv_cholesky(cuda_system, oracle, n):
     assert rel_fro(got @ G, np.eye(n)) <= 1e-8 * max(1.0, np.linalg.cond(G))
 
 
-def test_inv_singular_raises(cuda_system):
+def test_inv_singular_raises(cuda_system, monkeypatch):
+    """np.linalg.LinAlgError like the reference (numpy_compute.py:248-257).  Default: the status word is examined at
+    the next host synchronisation point (get / touch / synchronize); "eager": from the call itself."""
+    from nums_b200 import cuda_compute as cc
+    assert cc.CHECK_FACTORIZATION_STATUS == "deferred"
+    bad = cuda_system.inv(cuda_system.put(np.zeros((4, 4))), syskwargs={})
+    with pytest.raises(np.linalg.LinAlgError):
+        cuda_system.get(bad)
+    cuda_system.cholesky(cuda_system.put(-np.eye(3)), syskwargs={})
+    with pytest.raises(np.linalg.LinAlgError):
+        cuda_system.synchronize()
+    good = cuda_system.inv(cuda_system.put(np.eye(4) * 2.0), syskwargs={})
+    assert np.array_equal(cuda_system.get(good), np.eye(4) * 0.5)       # an examined failure does not linger
+    monkeypatch.setattr(cc, "CHECK_FACTORIZATION_STATUS", "eager")
     with pytest.raises(np.linalg.LinAlgError):
         cuda_system.inv(cuda_system.put(np.zeros((4, 4))), syskwargs={})
     with pytest.raises(np.linalg.LinAlgError):
