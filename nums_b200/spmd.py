@@ -26,6 +26,14 @@ launches the kernel.  What the host layers hold as ``oid`` is a ``Handle``: the 
   contracts its own terms in one grouped DMMA launch (CudaSystem's deferred contractions), and results whose
   terms live on several ranks are all-reduced; the stacked-R ``qr`` is a local QR + binary tree over the
   ranks + broadcast.  Results of cross-rank reductions are replicated.
+* **Shuffles / permutations** (SURVEY.md 8f.4): ``BlockArray._advanced_single_array_subscript``
+  (blockarray.py:229-316) builds every destination block as a CHAIN of ``update_block_along_axis(dst, src_j,
+  index_pairs_j, axis)`` calls, one per source block.  Executed call by call that ships every source block WHOLE
+  to every destination owner (G x the array over the links) and copies the destination G times.  The chains are
+  recorded instead (``_LazyScatter``) and materialised together: every source owner gathers just the rows a
+  destination asks for into a packed buffer (``nums_scatter_axis`` as a gather), ONE batched all-to-all moves
+  the packed rows (each row crosses the links at most once), and every destination owner copies its base block
+  once and scatters all its pieces into it.
 * ``get`` broadcasts from the home rank, so every rank's host program sees the same values (it may branch
   on them: ``if max(abs(g)) <= tol``, glms.py:370).
 
@@ -96,6 +104,16 @@ class _Lazy(object):
         return sorted({it[-1] for it in self.items})
 
 
+class _LazyScatter(object):
+    """value = ``base`` with, in order, ``dst[.., dst_idx, ..] = src[.., src_idx, ..]`` along ``axis`` for every
+    item (src handle, dst_idx, src_idx) -- the chain of update_block_along_axis calls that builds one block of a
+    shuffled array; evaluated on rank ``rank``."""
+    __slots__ = ("base", "items", "axis", "rank")
+
+    def __init__(self, base, items, axis, rank):
+        self.base, self.items, self.axis, self.rank = base, items, axis, rank
+
+
 # -----------------------------------------------------------------------------------------------------
 # local back ends: what SpmdSystem needs besides the kernel interface
 # -----------------------------------------------------------------------------------------------------
@@ -147,6 +165,34 @@ class _TorchBackend(object):
         n = int(np.prod(shape, dtype=np.int64))
         return buf[offset:offset + n].view(tuple(shape))
 
+    def take_along(self, v, index, axis):
+        """v[.., index, ..] along ``axis`` as a dense block (one nums_scatter_axis launch used as a gather)."""
+        import numpy as np_
+        from nums_b200 import cuda_compute as cc
+        v = self.system.contractions.resolve(v)
+        shape = list(v.shape)
+        outer = int(np_.prod(shape[:axis], dtype=np_.int64))
+        inner = int(np_.prod(shape[axis + 1:], dtype=np_.int64))
+        n = int(len(index))
+        out = cc._empty(shape[:axis] + [n] + shape[axis + 1:], cc._lib.numpy_dtype(v.dtype))
+        if n and out.numel():
+            cc._scatter(out, v, np_.arange(n, dtype=np_.int64), index, outer, n, shape[axis], inner)
+        return out
+
+    def scatter_chain(self, base, pieces, axis):
+        """A private copy of ``base`` with every (src, dst_index, src_index) of ``pieces`` applied in order."""
+        import numpy as np_
+        from nums_b200 import cuda_compute as cc
+        out = cc._materialize(self.system.contractions.resolve(base))
+        shape = tuple(out.shape)
+        outer = int(np_.prod(shape[:axis], dtype=np_.int64))
+        inner = int(np_.prod(shape[axis + 1:], dtype=np_.int64))
+        for src, dst_index, src_index in pieces:
+            src = self.system.contractions.resolve(src)
+            if len(dst_index) and out.numel():
+                cc._scatter(out, src, dst_index, src_index, outer, shape[axis], src.shape[axis], inner)
+        return out
+
     def flush(self):
         self.system.flush()
 
@@ -186,6 +232,17 @@ class _NumpyBackend(object):
     def flat_view(self, buf, offset, shape):
         n = int(np.prod(shape, dtype=np.int64))
         return buf[offset:offset + n].reshape(tuple(shape))
+
+    def take_along(self, v, index, axis):
+        return np.ascontiguousarray(np.take(np.asarray(v), np.asarray(index, dtype=np.int64), axis=axis))
+
+    def scatter_chain(self, base, pieces, axis):
+        out = np.array(base, copy=True)
+        for src, dst_index, src_index in pieces:
+            dst_sel = [slice(None)] * out.ndim
+            dst_sel[axis] = np.asarray(dst_index, dtype=np.int64)
+            out[tuple(dst_sel)] = np.take(np.asarray(src), np.asarray(src_index, dtype=np.int64), axis=axis)
+        return out
 
     def flush(self):
         pass
@@ -479,9 +536,11 @@ class SpmdSystem(object):
         self._bop_meta = {}
         self._owners = {}
         self._lazies = []
+        self._scatters = []                   # weakrefs to handles whose value is a _LazyScatter
         self._copied = weakref.WeakSet()      # handles with cached copies away from home
         self.stats = {"moves": 0, "moved_bytes": 0, "all_reduces": 0, "broadcasts": 0, "meta_broadcasts": 0,
-                      "executed": 0, "skipped": 0, "replicated": 0, "flushes": 0, "peer_exchanges": 0}
+                      "executed": 0, "skipped": 0, "replicated": 0, "flushes": 0, "peer_exchanges": 0,
+                      "scatter_chains": 0, "scatter_exchanges": 0, "scatter_moved_bytes": 0}
         self._peer = None
         if (isinstance(self.backend, _TorchBackend) and self.world_size > 1
                 and os.environ.get("NUMS_SPMD_PEER", "1") != "0"):
@@ -862,6 +921,8 @@ class SpmdSystem(object):
         if op == "add" and not t1 and not t2 and a1.dtype == _F64 and a2.dtype == _F64 \
                 and tuple(s1) == tuple(s2) == a1.shape == a2.shape:
             l1, l2 = a1.lazy, a2.lazy
+            if (l1 is not None and l1.__class__ is not _Lazy) or (l2 is not None and l2.__class__ is not _Lazy):
+                return _NOT_HANDLED                       # a pending shuffle: _generic materialises it first
             if l1 is not None or l2 is not None:
                 lazy_hint = (l1 or l2).hint
                 items = []
@@ -911,8 +972,105 @@ class SpmdSystem(object):
             return Handle._make(self._next, e, value, meta[0], meta[1])
         return _NOT_HANDLED
 
+    # -- shuffles: chains of update_block_along_axis recorded, then one gather / all-to-all / scatter ---------
+    def _k_update_block_along_axis(self, args, kwargs, sysk):
+        if kwargs or len(args) != 4 or self.world_size == 1:
+            return _NOT_HANDLED
+        dst, src, index_pairs, axis = args
+        if dst.__class__ is not Handle or src.__class__ is not Handle:
+            return _NOT_HANDLED
+        if src.lazy is not None or (dst.lazy is not None and dst.lazy.__class__ is not _LazyScatter):
+            return _NOT_HANDLED
+        nd = len(dst.shape)
+        if nd == 0 or len(src.shape) != nd:
+            return _NOT_HANDLED                           # shapes that only agree through broadcasting
+        axis = int(axis) % nd
+        if dst.shape[:axis] + dst.shape[axis + 1:] != src.shape[:axis] + src.shape[axis + 1:]:
+            return _NOT_HANDLED
+        pairs = list(index_pairs)
+        dst_idx = np.fromiter((int(p[0]) for p in pairs), dtype=np.int64, count=len(pairs))
+        src_idx = np.fromiter((int(p[1]) for p in pairs), dtype=np.int64, count=len(pairs))
+        if len(pairs) and (dst_idx.min() < 0 or src_idx.min() < 0 or dst_idx.max() >= dst.shape[axis]
+                           or src_idx.max() >= src.shape[axis]):
+            return _NOT_HANDLED                           # negative / out-of-range indices: the kernel's own checks
+        if dst.lazy is not None:
+            chain = dst.lazy
+            if chain.axis != axis:
+                return _NOT_HANDLED
+            base, items, rank = chain.base, chain.items + [(src, dst_idx, src_idx)], chain.rank
+        else:
+            hint = self._hint(sysk)
+            rank = dst.home if dst.home != REPLICATED else (0 if hint is None else hint)
+            base, items = dst, [(src, dst_idx, src_idx)]
+        self._next += 1
+        h = Handle._make(self._next, rank, None, dst.shape, dst.dtype)
+        h.lazy = _LazyScatter(base, items, axis, rank)
+        self._scatters.append(weakref.ref(h))
+        return h
+
+    def _flush_scatters(self):
+        """Materialise every pending shuffle chain that is still referenced (identical plan on every rank).
+        Intermediate links of a chain are dead by now (each call replaced ``dst_block.oid``), so only the last
+        handle of every chain does any work."""
+        alive = []
+        for ref in self._scatters:
+            h = ref()
+            if h is not None and h.lazy is not None and h.lazy.__class__ is _LazyScatter:
+                alive.append(h)
+        self._scatters = []
+        if not alive:
+            return
+        backend = self.backend
+        self.stats["scatter_chains"] += len(alive)
+        # A. rows that must travel: the source's owner packs them, one batched exchange moves them
+        sends, recvs, order = [], [], []
+        pieces = {}                                      # hid -> [(src block or packed rows, dst_idx, src_idx)]
+        for h in alive:
+            chain = h.lazy
+            mine = self.rank == chain.rank
+            plan = pieces.setdefault(h.hid, [])
+            for src, dst_idx, src_idx in chain.items:
+                if src.available_on(chain.rank):
+                    if mine:
+                        plan.append((src.value, dst_idx, src_idx))
+                    continue
+                n = int(len(dst_idx))
+                if n == 0:
+                    continue
+                packed_shape = src.shape[:chain.axis] + (n,) + src.shape[chain.axis + 1:]
+                nbytes = int(np.prod(packed_shape, dtype=np.int64)) * src.dtype.itemsize
+                order.append((src.home, chain.rank))
+                self.stats["scatter_moved_bytes"] += nbytes
+                if self.rank == src.home:
+                    sends.append((backend.take_along(src.value, src_idx, chain.axis), chain.rank))
+                elif mine:
+                    buf = backend.empty(packed_shape, src.dtype)
+                    recvs.append((buf, src.home))
+                    plan.append((buf, dst_idx, np.arange(n, dtype=np.int64)))
+        if order:
+            # a base block that lives elsewhere (not the case for BlockArray.empty results) travels whole, first
+            self.stats["scatter_exchanges"] += 1
+            self.comm.exchange(sends, recvs, order=order)
+        moves = [(h.lazy.base, h.lazy.rank) for h in alive if not h.lazy.base.available_on(h.lazy.rank)]
+        if moves:
+            self._move_many(moves)
+        # B. every destination owner: one copy of the base block, all pieces scattered into it
+        for h in alive:
+            chain = h.lazy
+            if self.rank == chain.rank:
+                h.value = backend.scatter_chain(chain.base.value, pieces[h.hid], chain.axis)
+            h.home = chain.rank
+            h.lazy = None
+
     def flush(self):
         """Materialise every lazy sum that is still referenced (identical plan on every rank)."""
+        if self._scatters:
+            self._flush_sums()
+            self._flush_scatters()
+            return
+        self._flush_sums()
+
+    def _flush_sums(self):
         alive = []
         for ref in self._lazies:
             h = ref()

@@ -129,7 +129,27 @@ def main():
     w = app.where(vb > app.scalar(1.5))
     checks["where_exact"] = bool(np.array_equal(w[0].get(), np.where(vals > 1.5)[0]))
 
+    # shuffles (test_np_random.py:46-106): chains of update_block_along_axis -> packed rows, one all-to-all
+    M = rng.standard_normal((4096, 96))
+    Mb = distributed(M, (512, 32))
+    perm0 = np.random.default_rng(5).permutation(4096)
+    perm1 = np.random.default_rng(6).permutation(96)[:50]
+    moved, rows = system.stats["moved_bytes"], system.stats["scatter_moved_bytes"]
+    S0 = Mb._advanced_single_array_subscript((perm0,), axis=0)
+    S1 = Mb._advanced_single_array_subscript((perm1,), axis=1)
+    checks["shuffle_rows_exact"] = bool(np.array_equal(S0.get(), M[perm0]))
+    checks["shuffle_cols_exact"] = bool(np.array_equal(S1.get(), M[:, perm1]))
+    checks["shuffle_whole_block_bytes"] = system.stats["moved_bytes"] - moved
+    checks["shuffle_row_bytes"] = system.stats["scatter_moved_bytes"] - rows
+    checks["shuffle_bytes_bound"] = (4096 * 96 + 4096 * 50) * 8
+    ivals = np.arange(100_000, dtype=np.int64)
+    ib = distributed(ivals, (12_500,))
+    permv = np.random.default_rng(9).permutation(100_000)
+    checks["shuffle_int_vector_exact"] = bool(np.array_equal(ib[permv].get(), ivals[permv]))
+
     ok = (checks["add_exact"] and checks["mul_exact"] and checks["elementwise_moved_bytes"] == 0
+          and checks["shuffle_rows_exact"] and checks["shuffle_cols_exact"] and checks["shuffle_int_vector_exact"]
+          and checks["shuffle_whole_block_bytes"] == 0 and 0 < checks["shuffle_row_bytes"] <= checks["shuffle_bytes_bound"]
           and checks["matmul_homes_ok"] and checks["matmul_rel"] <= 1e-10 and checks["matmul_again_rel"] <= 1e-10
           and checks["gram_rel"] <= 1e-10 and checks["sum_axis0_rel"] <= 1e-12 and checks["max_exact"]
           and checks["sum_all_rel"] <= 1e-12 and checks["R_replicated"] and checks["R_rel"] <= 1e-10

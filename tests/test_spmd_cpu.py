@@ -128,6 +128,25 @@ def _worker(rank, world, port, results):
         out["where"] = [w.get() for w in app.where(vb > app.scalar(0.5))]
         rs = app.random_state(1337)
         out["random"] = rs.random((64, 4), (16, 4)).get()
+        # ---- shuffles (test_np_random.py:46-106): update_block_along_axis chains -> packed rows, one all-to-all ----
+        M = rng.standard_normal((96, 40))
+        Mb = app.array(M, (12, 10)) + app.zero                       # 8 x 4 blocks living on their owners
+        perm0 = np.random.default_rng(5).permutation(96)
+        perm1 = np.random.default_rng(6).permutation(40)[:25]
+        before = dict(system.stats)
+        S0 = Mb._advanced_single_array_subscript((perm0,), axis=0)
+        S1 = Mb._advanced_single_array_subscript((perm1,), axis=1)
+        system.flush()
+        out["shuffle_homes"] = [S0.blocks[e].oid.home for e in S0.grid.get_entry_iterator()]   # (get() replicates small blocks)
+        out["shuffle0"], out["shuffle1"] = S0.get(), S1.get()
+        out["_M"] = M
+        out["shuffle_whole_block_moves"] = system.stats["moved_bytes"] - before["moved_bytes"]
+        out["shuffle_row_bytes"] = system.stats["scatter_moved_bytes"] - before["scatter_moved_bytes"]
+        out["shuffle_exchanges"] = system.stats["scatter_exchanges"] - before["scatter_exchanges"]
+        out["shuffle_owners"] = [system.owner(e, S0.grid.grid_shape) for e in S0.grid.get_entry_iterator()]
+        Vb = app.array(vals, (125,)) + app.zero
+        out["shuffle_vec"] = Vb[np.random.default_rng(8).permutation(1000)].get()
+        out["shuffle_then_sum"] = app.sum(S0 + S0, axis=0).get()      # a pending chain consumed by another kernel
         out["stats"] = dict(system.stats)
         results[rank] = out
     finally:
@@ -174,6 +193,14 @@ def test_reference_host_layers_over_spmd(world):
         assert r["argmax"] == int(np.argmax(vals))
         assert len(r["where"]) == 1 and np.array_equal(r["where"][0], np.where(vals > 0.5)[0])
         assert np.array_equal(r["random"], results[0]["random"])          # same stream on every rank
+        assert np.array_equal(r["shuffle0"], r["_M"][np.random.default_rng(5).permutation(96)])
+        assert np.array_equal(r["shuffle1"], r["_M"][:, np.random.default_rng(6).permutation(40)[:25]])
+        assert np.array_equal(r["shuffle_vec"], vals[np.random.default_rng(8).permutation(1000)])
+        assert np.allclose(r["shuffle_then_sum"], 2 * r["_M"].sum(axis=0), rtol=1e-12, atol=1e-12)
+        assert r["shuffle_homes"] == r["shuffle_owners"]                  # destination blocks live on their owners
+        assert r["shuffle_whole_block_moves"] == 0                        # no source block travelled whole
+        assert 0 < r["shuffle_row_bytes"] <= (96 * 40 + 96 * 25) * 8      # every row crossed the links at most once
+        assert r["shuffle_exchanges"] <= 3
         # Newton LR: nothing but all-reduces crosses ranks (X and y never move)
         assert r["lr_moved_bytes"] == 0, r["lr_moved_bytes"]
         assert r["lr_all_reduces"] >= 6
