@@ -48,6 +48,18 @@ elif which == "rowcol":       # (n, 1) * (n, 28): the s * X of the LR Hessian (g
     col = torch.randn((n, 1), dtype=torch.float64, device=dev)
     for _ in range(4):
         w = system.bop("mul", col, X, (n, 1), (n, d), False, False, axes=None, syskwargs={})
+elif which == "skinny":       # X^T (s X) of the LR Hessian (glms.py:232-238) on one config-4 block: 28 x n_b by n_b x 28
+    n, d = 1_375_000, 28
+    X = torch.randn((n, d), dtype=torch.float64, device=dev)
+    S = torch.randn((n, d), dtype=torch.float64, device=dev)
+    for _ in range(4):
+        h = system.bop("tensordot", X, S, (d, n), (n, d), True, False, axes=1, syskwargs={})
+elif which == "gemvn":        # X beta (glms.py:140-143) on one config-4 block
+    n, d = 1_375_000, 28
+    X = torch.randn((n, d), dtype=torch.float64, device=dev)
+    b = torch.randn((d,), dtype=torch.float64, device=dev)
+    for _ in range(4):
+        z = system.bop("tensordot", X, b, (n, d), (d,), False, False, axes=1, syskwargs={})
 elif which == "qr":
     X = torch.randn((262144, 128), dtype=torch.float64, device=dev)
     for _ in range(2):
