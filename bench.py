@@ -1253,7 +1253,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-workloads", action="store_true", help="only the headline matmul")
     ap.add_argument("--quick", action="store_true", help="fewer repetitions of the secondary workloads")
-    ap.add_argument("--watchdog", type=int, default=900,
+    ap.add_argument("--watchdog", type=int, default=420,
                     help="seconds the secondary workloads may take before the headline line is printed without them")
     ap.add_argument("--large", action="store_true", help="config 5 instead: 65536^2 matmul (one-off record run)")
     ap.add_argument("--summa-driver", action="store_true",

@@ -895,7 +895,9 @@ newton_step_warp_kernel(int d, const double* __restrict__ gh, const double* __re
   double* mine = aug + lane * P;
   int failed = 0;
   for (int k = 0; k < d; ++k) {
-    double best = (live && lane >= k) ? fabs(mine[k]) : -1.0;
+    // first maximum of |a[i][k]|, i >= k; a NaN never wins a comparison (as in the kernel above: `a > best`)
+    const double cand = (live && lane >= k) ? fabs(mine[k]) : -1.0;
+    double best = cand > -1.0 ? cand : -1.0;
     int bi = lane;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -906,9 +908,11 @@ newton_step_warp_kernel(int d, const double* __restrict__ gh, const double* __re
         bi = oi;
       }
     }
+    best = __shfl_sync(0xffffffffu, best, 0);     // (every lane holds the same pair already; make it explicit)
+    bi = __shfl_sync(0xffffffffu, bi, 0);
     if (!(best > 0.0)) {
       if (failed == 0) failed = k + 1;
-      if (best < 0.0) bi = k;           // a NaN column: every comparison failed; keep the diagonal like the kernel above
+      if (best < 0.0) bi = k;           // nothing but NaNs below the diagonal: keep the diagonal like the kernel above
     }
     const int p = bi;
     if (p != k) {                       // uniform: lanes swap the two rows column-wise

@@ -47,20 +47,30 @@ _SHORT_OP_NAMES = {
 #       exactly where NumPy would (NUMS_FACTORIZATION_STATUS=eager);
 #   "off"   -- never checked.
 CHECK_FACTORIZATION_STATUS = __import__("os").environ.get("NUMS_FACTORIZATION_STATUS", "deferred")
-_PENDING_STATUS = []          # [(int32 device scalar, message)] of factorizations not yet examined
+_PENDING_STATUS = []          # [(device scalar, exception to raise if it is "bad")] of kernels not yet examined
 _PENDING_STATUS_MAX = 64
 
 
 def check_pending_status():
-    """Examine the status words of every factorization launched since the last check (the caller has
-    synchronised, or is about to: each read is a 4-byte copy).  Raises LinAlgError for the first failure."""
+    """Examine the status words of every data-dependent error check launched since the last look (the caller has
+    synchronised, or is about to: each read is a few bytes).  Raises the first failure: LinAlgError for a singular /
+    non-positive-definite factorization (status word != 0), ValueError for an integer power with a negative
+    exponent (minimum of the exponent block < 0)."""
     if not _PENDING_STATUS:
         return
     pending = list(_PENDING_STATUS)
     del _PENDING_STATUS[:]
-    for info, message in pending:
-        if int(info.cpu().item()) != 0:
-            raise np.linalg.LinAlgError(message)
+    for word, bad, exc in pending:
+        if bad(word.cpu().item()):
+            raise exc
+
+
+def _nonzero(v):
+    return int(v) != 0
+
+
+def _negative(v):
+    return v < 0
 
 
 class RNG(_RNGInterface):
@@ -832,7 +842,10 @@ def elementwise(name, a1, a2):
             raise NotImplementedError("binary ufunc %s" % name)
         loop, out_dt = bop_types(name, _lib.numpy_dtype(a1.dtype), _lib.numpy_dtype(a2.dtype))
         plan = _BOP_PLANS[key] = (_lib.BOP_CODE[name], _lib.dtype_code(loop), _lib.torch_dtype(out_dt),
-                                  _lib.dtype_code(a1.dtype), _lib.dtype_code(a2.dtype), _lib.dtype_code(out_dt))
+                                  _lib.dtype_code(a1.dtype), _lib.dtype_code(a2.dtype), _lib.dtype_code(out_dt),
+                                  name == "power" and np.dtype(loop).kind in "iu")
+    if plan[6] and a2.numel():
+        _check_integer_exponent(a2)
     s1, s2 = a1.shape, a2.shape
     shape = s1 if s1 == s2 else _broadcast_shape(tuple(s1), tuple(s2))
     out = torch.empty(shape, dtype=plan[2], device=a1.device)
@@ -848,6 +861,22 @@ def elementwise(name, a1, a2):
         if rc:
             LIB.check(rc)
     return out
+
+
+def _check_integer_exponent(exponent):
+    """np.power on integers raises ValueError("Integers to negative integer powers are not allowed.") when any
+    exponent is negative -- a property of the DATA.  The minimum of the exponent block is reduced on the device and
+    looked at with the other deferred status words (check_pending_status) at the next host synchronisation."""
+    if exponent.dtype == torch.bool:
+        return
+    src = exponent if exponent.is_contiguous() else _materialize(exponent)
+    low = _empty((), _lib.numpy_dtype(src.dtype))
+    code = _lib.dtype_code(src.dtype)
+    LIB.call_ws(LIB.dll.nums_reduce, src.device,
+                ((_lib.REDUCE_CODE["min"], src.data_ptr(), code, 1, src.numel(), 1, low.data_ptr(), code), (_stream(),)))
+    _PENDING_STATUS.append((low, _negative, ValueError("Integers to negative integer powers are not allowed.")))
+    if len(_PENDING_STATUS) > _PENDING_STATUS_MAX:
+        check_pending_status()
 
 
 def _as_matrix(t, rows, cols):
@@ -1161,7 +1190,7 @@ def _single_cta_factor(fn, arr, message):
             if int(info.cpu().item()) != 0:
                 raise np.linalg.LinAlgError(message)
         else:
-            _PENDING_STATUS.append((info, message))
+            _PENDING_STATUS.append((info, _nonzero, np.linalg.LinAlgError(message)))
             if len(_PENDING_STATUS) > _PENDING_STATUS_MAX:
                 check_pending_status()
     return out

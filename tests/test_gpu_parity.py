@@ -644,6 +644,29 @@ def test_inv_singular_raises(cuda_system, monkeypatch):
         cuda_system.cholesky(cuda_system.put(-np.eye(3)), syskwargs={})
 
 
+def test_integer_power_negative_exponent_raises(cuda_system, oracle):
+    """np.power(int, negative int) raises ValueError in the reference (numpy_compute.py:233-238 -> NumPy); here the
+    check is a device-side minimum examined at the next host synchronisation."""
+    base = np.arange(1, 9, dtype=np.int64)
+    good = np.array([0, 1, 2, 3, 0, 1, 2, 3], dtype=np.int64)
+    got = cuda_system.get(cuda_system.bop("pow", cuda_system.put(base), cuda_system.put(good), (8,), (8,), False, False,
+                                          axes=None, syskwargs={}))
+    assert_exact(got, oracle.bop("pow", base, good, (8,), (8,), False, False, None))
+    bad = good.copy()
+    bad[5] = -1
+    with pytest.raises(ValueError):
+        oracle.bop("pow", base, bad, (8,), (8,), False, False, None)
+    out = cuda_system.bop("pow", cuda_system.put(base), cuda_system.put(bad), (8,), (8,), False, False, axes=None,
+                          syskwargs={})
+    with pytest.raises(ValueError):
+        cuda_system.get(out)
+    # float bases take negative exponents like NumPy
+    fb = base.astype(np.float64)
+    got = cuda_system.get(cuda_system.bop("pow", cuda_system.put(fb), cuda_system.put(bad), (8,), (8,), False, False,
+                                          axes=None, syskwargs={}))
+    assert np.allclose(got, fb ** bad, rtol=1e-15)
+
+
 # ----------------------------------------------------------------------------------------------------
 # fused LR kernel vs the reference composition (glms.py:213-240)
 # ----------------------------------------------------------------------------------------------------
