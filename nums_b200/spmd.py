@@ -534,6 +534,7 @@ class SpmdSystem(object):
         self._registered = set()
         self._next = 0
         self._bop_meta = {}
+        self._infer_memo = {}
         self._owners = {}
         self._lazies = []
         self._scatters = []                   # weakrefs to handles whose value is a _LazyScatter
@@ -836,7 +837,67 @@ class SpmdSystem(object):
                 return out
         return self._generic(name, args, kwargs, sysk, rank)
 
+    def _colocated(self, name, args, kwargs):
+        """Fast path of ``_generic`` for the common case of the per-block kernels (map_uop, reduce_axis, GEMV-shaped
+        tensordot, lr_grad_hess, ...): positional block arguments only, nothing lazy, no cached copies, and every
+        operand that is not replicated lives on ONE rank.  That rank executes (the same answer ``_exec_rank`` gives:
+        it holds all the operand bytes), nothing has to move, and the result description comes from a memo of
+        ``infer_result`` keyed by the call's shapes / dtypes / scalar arguments.  ``_NOT_HANDLED`` for anything else."""
+        e = REPLICATED
+        key = [name]
+        for a in args:
+            if a.__class__ is Handle:
+                if a.lazy is not None or a.copies:
+                    return _NOT_HANDLED
+                if a.home != REPLICATED:
+                    if e == REPLICATED:
+                        e = a.home
+                    elif a.home != e:
+                        return _NOT_HANDLED
+                key.append((a.shape, a.dtype))
+            elif a is None or a.__class__ in (str, int, bool, float):
+                key.append(a)
+            elif a.__class__ is tuple and len(a) <= 8 and all(x.__class__ in (int, str, bool, float) for x in a):
+                key.append(a)
+            elif (a.__class__ is tuple or a.__class__ is dict) and not a:
+                key.append(())
+            else:
+                return _NOT_HANDLED
+        if e == REPLICATED:
+            return _NOT_HANDLED                      # all replicated: the generic path decides (may replicate the call)
+        for k, v in kwargs.items():
+            if v is None or v.__class__ in (str, int, bool, float):
+                key.append((k, v))
+            else:
+                return _NOT_HANDLED
+        key = tuple(key)
+        desc = self._infer_memo.get(key)
+        if desc is None:
+            desc = infer_result(name, args, kwargs, self._meta_of)
+            if desc is None:
+                return _NOT_HANDLED
+            if len(self._infer_memo) < 8192:
+                self._infer_memo[key] = desc
+        result = None
+        if self.rank == e:
+            self.stats["executed"] += 1
+            result = self.local.call(name, *[a.value if a.__class__ is Handle else a for a in args], **kwargs)
+            if self.check:
+                actual = self._describe(result)
+                if actual != desc:
+                    raise AssertionError("SPMD result inference mismatch for %s: inferred %r, actual %r" % (name, desc, actual))
+        else:
+            self.stats["skipped"] += 1
+        if desc[0] == "b":
+            self._next += 1
+            return Handle._make(self._next, e, result, desc[1], np.dtype(desc[2]))
+        return self._wrap(result, desc, e)
+
     def _generic(self, name, args, kwargs, sysk, rank=None):
+        if rank is None and name not in self._registered:
+            out = self._colocated(name, args, kwargs)
+            if out is not _NOT_HANDLED:
+                return out
         handles = self._handles_in(args, kwargs)
         if any(h.lazy is not None for h in handles):
             self.flush()
