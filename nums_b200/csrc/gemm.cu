@@ -950,6 +950,150 @@ int launch_skinny_dense(const double* A, const double* B, int M, int N, int64_t 
   return launch_fold_partials(static_cast<const double*>(ws), grid, M, N, Cin, ldcin, C, ldc, s);
 }
 
+// --------------------------------------------------------------------------------------
+// Gram matrix of a tall dense block with 128 columns: C = A^T A  (the TSQR leaf on the Gram path, config 3:
+// cuda_compute._gram_of; application.py:784-814 asks for qr(block, mode="r") of 2 097 152 x 128 blocks).
+// The general GEMM computes all 256 8x8 blocks of the 128 x 128 result; by symmetry only the 136 on or above the
+// block diagonal are needed, and because the m8n8k4 A and B fragments of A^T A are the SAME registers (lane (g, t)
+// holds X[row t][8 c + g] for block column c either way) a warp that owns block row r needs no operand beyond the
+// fragments of the block columns it multiplies with.  Block rows are paired so that every one of the eight MMA
+// warps owns 17 blocks: warp w takes block row w (16 - w blocks) and block row 15 - w (w + 1 blocks) and loads
+// 16 - w fragments per rank-4 update.  All warps consume the same 64-row chunk; a producer warp feeds a 3-deep
+// ring with one bulk copy per ROW (1 KB) into rows padded to 132 doubles (pitch = 4 mod 16: conflict-free
+// fragment reads; a dense 128-double pitch would put rows t = 0..3 of a fragment on the same banks).  Tensor-pipe
+// time is 136 / 256 of the GEMM's: 2 m n^2 "flops" in the time of 1.06 m n^2.
+// --------------------------------------------------------------------------------------
+constexpr int kSyrkN = 128;
+constexpr int kSyrkRows = 64;
+constexpr int kSyrkStages = 3;
+constexpr int kSyrkPitch = kSyrkN + 4;
+constexpr int kSyrkThreads = 256 + 32;
+constexpr int kSyrkStageDoubles = kSyrkRows * kSyrkPitch;
+
+template <int W>
+__device__ __forceinline__ void syrk_consumer(double* ring, uint64_t* full, uint64_t* empty, int64_t K, int64_t my_chunks,
+                                              int lane) {
+  constexpr int NB = kSyrkN / 8;             // 16 block columns
+  constexpr int R1 = NB - 1 - W;             // the second block row of this warp
+  const int g = lane >> 2, t = lane & 3;
+  double acc0[NB - W][2], acc1[W + 1][2];
+#pragma unroll
+  for (int c = 0; c < NB - W; ++c) acc0[c][0] = acc0[c][1] = 0.0;
+#pragma unroll
+  for (int c = 0; c < W + 1; ++c) acc1[c][0] = acc1[c][1] = 0.0;
+  for (int64_t i = 0; i < my_chunks; ++i) {
+    const int slot = (int)(i % kSyrkStages);
+    mbar_wait(&full[slot], (uint32_t)((i / kSyrkStages) & 1));
+    const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * kSyrkRows;
+    const int rows = (int)((K - r0 < kSyrkRows) ? (K - r0) : kSyrkRows);
+    const double* tile = ring + (size_t)slot * kSyrkStageDoubles;
+#pragma unroll 4
+    for (int q = 0; q < kSyrkRows / 4; ++q) {
+      const bool row_ok = 4 * q + t < rows;       // rows past the end of the last chunk hold stale data
+      const double* xr = tile + (4 * q + t) * kSyrkPitch + g;
+      double f[NB];
+#pragma unroll
+      for (int c = W; c < NB; ++c) {
+        const double v = xr[8 * c];
+        f[c] = row_ok ? v : 0.0;
+      }
+#pragma unroll
+      for (int c = W; c < NB; ++c) dmma884(acc0[c - W], f[W], f[c]);
+#pragma unroll
+      for (int c = R1; c < NB; ++c) dmma884(acc1[c - R1], f[R1], f[c]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
+  }
+  // every warp waits until all chunks are consumed by everybody, then the ring becomes the 128 x 128 result image
+  asm volatile("bar.sync 1, 256;\n" ::: "memory");
+  double* img = ring;
+#pragma unroll
+  for (int c = W; c < NB; ++c) {
+    img[(8 * W + g) * kSyrkN + 8 * c + 2 * t] = acc0[c - W][0];
+    img[(8 * W + g) * kSyrkN + 8 * c + 2 * t + 1] = acc0[c - W][1];
+  }
+#pragma unroll
+  for (int c = R1; c < NB; ++c) {
+    img[(8 * R1 + g) * kSyrkN + 8 * c + 2 * t] = acc1[c - R1][0];
+    img[(8 * R1 + g) * kSyrkN + 8 * c + 2 * t + 1] = acc1[c - R1][1];
+  }
+}
+
+__global__ void __launch_bounds__(kSyrkThreads, 1)
+dsyrk128_stream_kernel(const double* __restrict__ A, int64_t K, double* __restrict__ partial) {
+  extern __shared__ __align__(128) double syrk_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* ring = syrk_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)kSyrkStages * kSyrkStageDoubles);
+  uint64_t* empty = full + kSyrkStages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSyrkStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t nchunks = (K + kSyrkRows - 1) / kSyrkRows;
+  const int64_t my_chunks = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (warp == 8) {
+    for (int64_t i = 0; i < my_chunks; ++i) {
+      const int slot = (int)(i % kSyrkStages);
+      const int64_t round = i / kSyrkStages;
+      const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * kSyrkRows;
+      const int rows = (int)((K - r0 < kSyrkRows) ? (K - r0) : kSyrkRows);
+      if (lane == 0) {
+        if (round > 0) {
+          mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before async writes
+        }
+        mbar_expect_tx(&full[slot], (uint32_t)(rows * kSyrkN * sizeof(double)));
+      }
+      __syncwarp();
+      double* dst = ring + (size_t)slot * kSyrkStageDoubles;
+      for (int r = lane; r < rows; r += 32)
+        bulk_copy_g2s(dst + r * kSyrkPitch, A + (r0 + r) * kSyrkN, (uint32_t)(kSyrkN * sizeof(double)), &full[slot]);
+    }
+  } else {
+    switch (warp) {
+      case 0: syrk_consumer<0>(ring, full, empty, K, my_chunks, lane); break;
+      case 1: syrk_consumer<1>(ring, full, empty, K, my_chunks, lane); break;
+      case 2: syrk_consumer<2>(ring, full, empty, K, my_chunks, lane); break;
+      case 3: syrk_consumer<3>(ring, full, empty, K, my_chunks, lane); break;
+      case 4: syrk_consumer<4>(ring, full, empty, K, my_chunks, lane); break;
+      case 5: syrk_consumer<5>(ring, full, empty, K, my_chunks, lane); break;
+      case 6: syrk_consumer<6>(ring, full, empty, K, my_chunks, lane); break;
+      default: syrk_consumer<7>(ring, full, empty, K, my_chunks, lane); break;
+    }
+  }
+  __syncthreads();
+  // the blocks on or above the block diagonal were computed; everything below is their mirror image
+  double* out = partial + (size_t)blockIdx.x * kSyrkN * kSyrkN;
+  for (int e = threadIdx.x; e < kSyrkN * kSyrkN; e += kSyrkThreads) {
+    const int r = e / kSyrkN, c = e - r * kSyrkN;
+    out[e] = (r / 8 <= c / 8) ? ring[r * kSyrkN + c] : ring[c * kSyrkN + r];
+  }
+}
+
+inline bool syrk_stream_enabled() {   // NUMS_SYRK_STREAM=0 sends A^T A through the general GEMM (A/B measurements)
+  static const bool on = []() { const char* v = getenv("NUMS_SYRK_STREAM"); return !(v && v[0] == '0'); }();
+  return on;
+}
+
+int launch_syrk128(const double* A, int64_t K, const double* Cin, int64_t ldcin, double* C, int64_t ldc, void* ws,
+                   size_t ws_bytes, cudaStream_t s) {
+  const size_t smem = (size_t)kSyrkStages * kSyrkStageDoubles * sizeof(double) + 2 * kSyrkStages * sizeof(uint64_t);
+  const int64_t nchunks = (K + kSyrkRows - 1) / kSyrkRows;
+  int grid = sm_count();
+  if (grid > nchunks) grid = (int)nchunks;
+  NUMS_NEED_WS((size_t)grid * kSyrkN * kSyrkN * sizeof(double), ws_bytes);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(dsyrk128_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dsyrk128_stream_kernel<<<grid, kSyrkThreads, smem, s>>>(A, K, static_cast<double*>(ws));
+  NUMS_LAUNCH_OK();
+  return launch_fold_partials(static_cast<const double*>(ws), grid, kSyrkN, kSyrkN, Cin, ldcin, C, ldc, s);
+}
+
 template <int MB, int NB>
 int launch_skinny(const double* A, int64_t lda, const double* B, int64_t ldb, int M, int N, int64_t K,
                   const double* Cin, int64_t ldcin, double* C, int64_t ldc, void* ws, size_t ws_bytes,
@@ -1582,6 +1726,9 @@ int run_gemm_typed(int ta, int tb, int64_t M, int64_t N, int64_t K, const T* A, 
     const bool aligned = dmma_operand_ok(A, lda) && dmma_operand_ok(B, ldb);
     if (aligned && ta && !tb && M <= 32 && N <= 32 && M % 2 == 0 && N % 2 == 0 && K >= 8192)
       return run_skinny(A, lda, B, ldb, M, N, K, Cin, ldc, C, ldc, ws, ws_bytes, s);
+    if (aligned && ta && !tb && A == B && M == kSyrkN && N == kSyrkN && lda == kSyrkN && ldb == kSyrkN && K >= 16384
+        && syrk_stream_enabled())
+      return launch_syrk128(A, K, Cin, ldc, C, ldc, ws, ws_bytes, s);
     const bool worthwhile = M * N >= 32 * 32 || K >= 4096;
     if (aligned && worthwhile)
       return run_dgemm(ta, tb, M, N, K, A, lda, B, ldb, Cin, ldc, C, ldc, ws, ws_bytes, s);

@@ -510,6 +510,8 @@ def tsqr_r_tree(system, comm, local_row_blocks, n):
     rs = [system.qr(b, mode="r", axis=1, syskwargs={"grid_entry": (i, 0), "grid_shape": (len(local_row_blocks), 1)})
           for i, b in enumerate(local_row_blocks)]
     r = rs[0] if len(rs) == 1 else system.qr(*rs, mode="r", axis=0, syskwargs={"grid_entry": (0, 0), "grid_shape": (1, 1)})
+    if hasattr(r, "materialize"):         # cuda_compute.DeferredR: a block's R that so far exists only as its Gram matrix
+        r = r.materialize()
     step = 1
     while step < comm.world:
         if comm.rank % (2 * step) == step:

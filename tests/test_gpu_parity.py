@@ -511,6 +511,25 @@ def test_tensordot_skinny_dense_and_narrow_gemv(cuda_system, oracle, k):
     _tdot(cuda_system, oracle, u, v)
 
 
+@pytest.mark.parametrize("k", [16384, 16384 + 37, 100_000, 1 << 20])
+def test_gram_128_streaming_syrk(cuda_system, k):
+    """A^T A of a tall dense 128-column block (the TSQR leaf on the Gram path, cuda_compute._gram_of): the streaming
+    kernel computes the 136 blocks on or above the block diagonal and mirrors the rest."""
+    from nums_b200 import cuda_compute as cc
+    rng = np.random.default_rng(k)
+    A = rng.standard_normal((k, 128))
+    t = cuda_system.put(A)
+    gram = cuda_system.get(cc._gram_of(t))
+    want = A.T @ A
+    assert rel_fro(gram, want) <= GEMM_TOL
+    assert np.array_equal(gram, gram.T)
+    # R through the public entry: qr(mode="r") on the Gram path
+    R = cuda_system.get(cuda_system.qr(t, mode="r", syskwargs={}))
+    Rref = np.linalg.qr(A, mode="r")
+    sg = np.sign(np.diag(R)) * np.sign(np.diag(Rref))
+    assert rel_fro(R * sg[:, None], Rref) <= 1e-10
+
+
 def test_tensordot_int_f32_nd(cuda_system, oracle):
     A = np.arange(6 * 7, dtype=np.int64).reshape(6, 7)       # test_bop.py:38-42 uses arange matrices
     B = np.arange(7 * 5, dtype=np.int64).reshape(7, 5)
