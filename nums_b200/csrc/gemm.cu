@@ -652,9 +652,42 @@ fold_partials_warp_kernel(const double* __restrict__ partial, int splits, int64_
   }
 }
 
+// Larger results (the 128 x 128 Gram matrix: 16384 elements x ~148 partials): a CTA folds 32 consecutive elements,
+// eight threads per element each adding every eighth partial (coalesced 256-byte rows), then a fixed-order sum of the
+// eight through shared memory -- deterministic.
+__global__ void __launch_bounds__(256)
+fold_partials_tiled_kernel(const double* __restrict__ partial, int splits, int64_t M, int64_t N,
+                           const double* __restrict__ cin, int64_t ldcin, double* __restrict__ out, int64_t ldc) {
+  __shared__ double part[8][32];
+  const int e = threadIdx.x & 31, sg = threadIdx.x >> 5;
+  const int64_t total = M * N;
+  const int64_t i = (int64_t)blockIdx.x * 32 + e;
+  double a0 = 0.0, a1 = 0.0;
+  if (i < total) {
+    int s = sg;
+    for (; s + 8 < splits; s += 16) {
+      a0 += partial[(int64_t)s * total + i];
+      a1 += partial[(int64_t)(s + 8) * total + i];
+    }
+    if (s < splits) a0 += partial[(int64_t)s * total + i];
+  }
+  part[sg][e] = a0 + a1;
+  __syncthreads();
+  if (sg == 0 && i < total) {
+    double acc = part[0][e];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) acc += part[q][e];
+    const int64_t m = i / N, n = i - m * N;
+    if (cin != nullptr) acc += cin[m * ldcin + n];
+    out[m * ldc + n] = acc;
+  }
+}
+
 inline int launch_fold_partials(const double* partial, int splits, int64_t M, int64_t N, const double* cin,
                                 int64_t ldcin, double* out, int64_t ldc, cudaStream_t s) {
-  if (splits >= 16 && M * N <= 4096) {
+  if (splits >= 16 && M * N > 4096 && M * N <= (1 << 20)) {
+    fold_partials_tiled_kernel<<<(unsigned)ceil_div(M * N, 32), 256, 0, s>>>(partial, splits, M, N, cin, ldcin, out, ldc);
+  } else if (splits >= 16 && M * N <= 4096) {
     fold_partials_warp_kernel<<<(unsigned)ceil_div(M * N, 8), 256, 0, s>>>(partial, splits, M, N, cin, ldcin, out, ldc);
   } else {
     splitk_fold_kernel<<<blocks_for(M * N, 256, (int64_t)sm_count() * 8), 256, 0, s>>>(partial, splits, M, N, cin, ldcin,
@@ -963,6 +996,8 @@ int launch_skinny_dense(const double* A, const double* B, int M, int N, int64_t 
 // fragment reads; a dense 128-double pitch would put rows t = 0..3 of a fragment on the same banks).  Tensor-pipe
 // time is 136 / 256 of the GEMM's: 2 m n^2 "flops" in the time of 1.06 m n^2.
 // --------------------------------------------------------------------------------------
+bool encode_matrix_map(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                       int box_cols);
 constexpr int kSyrkN = 128;
 constexpr int kSyrkRows = 64;
 constexpr int kSyrkStages = 3;
@@ -972,7 +1007,7 @@ constexpr int kSyrkStageDoubles = kSyrkRows * kSyrkPitch;
 
 template <int W>
 __device__ __forceinline__ void syrk_consumer(double* ring, uint64_t* full, uint64_t* empty, int64_t K, int64_t my_chunks,
-                                              int lane) {
+                                              int lane, bool zero_filled) {
   constexpr int NB = kSyrkN / 8;             // 16 block columns
   constexpr int R1 = NB - 1 - W;             // the second block row of this warp
   const int g = lane >> 2, t = lane & 3;
@@ -987,20 +1022,34 @@ __device__ __forceinline__ void syrk_consumer(double* ring, uint64_t* full, uint
     const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * kSyrkRows;
     const int rows = (int)((K - r0 < kSyrkRows) ? (K - r0) : kSyrkRows);
     const double* tile = ring + (size_t)slot * kSyrkStageDoubles;
+    if (rows == kSyrkRows || zero_filled) {       // (uniform) every chunk but possibly the last
 #pragma unroll 4
-    for (int q = 0; q < kSyrkRows / 4; ++q) {
-      const bool row_ok = 4 * q + t < rows;       // rows past the end of the last chunk hold stale data
-      const double* xr = tile + (4 * q + t) * kSyrkPitch + g;
-      double f[NB];
+      for (int q = 0; q < kSyrkRows / 4; ++q) {
+        const double* xr = tile + (4 * q + t) * kSyrkPitch + g;
+        double f[NB];
 #pragma unroll
-      for (int c = W; c < NB; ++c) {
-        const double v = xr[8 * c];
-        f[c] = row_ok ? v : 0.0;
+        for (int c = W; c < NB; ++c) f[c] = xr[8 * c];
+#pragma unroll
+        for (int c = W; c < NB; ++c) dmma884(acc0[c - W], f[W], f[c]);
+#pragma unroll
+        for (int c = R1; c < NB; ++c) dmma884(acc1[c - R1], f[R1], f[c]);
       }
+    } else {
+#pragma unroll 2
+      for (int q = 0; q < kSyrkRows / 4; ++q) {
+        const bool row_ok = 4 * q + t < rows;     // rows past the end of the last chunk hold stale data
+        const double* xr = tile + (4 * q + t) * kSyrkPitch + g;
+        double f[NB];
 #pragma unroll
-      for (int c = W; c < NB; ++c) dmma884(acc0[c - W], f[W], f[c]);
+        for (int c = W; c < NB; ++c) {
+          const double v = xr[8 * c];
+          f[c] = row_ok ? v : 0.0;
+        }
 #pragma unroll
-      for (int c = R1; c < NB; ++c) dmma884(acc1[c - R1], f[R1], f[c]);
+        for (int c = W; c < NB; ++c) dmma884(acc0[c - W], f[W], f[c]);
+#pragma unroll
+        for (int c = R1; c < NB; ++c) dmma884(acc1[c - R1], f[R1], f[c]);
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[slot]);
@@ -1021,7 +1070,8 @@ __device__ __forceinline__ void syrk_consumer(double* ring, uint64_t* full, uint
 }
 
 __global__ void __launch_bounds__(kSyrkThreads, 1)
-dsyrk128_stream_kernel(const double* __restrict__ A, int64_t K, double* __restrict__ partial) {
+dsyrk128_stream_kernel(const double* __restrict__ A, int64_t K, double* __restrict__ partial,
+                       const __grid_constant__ CUtensorMap map, int use_map) {
   extern __shared__ __align__(128) double syrk_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* ring = syrk_smem;
@@ -1043,28 +1093,38 @@ dsyrk128_stream_kernel(const double* __restrict__ A, int64_t K, double* __restri
       const int64_t round = i / kSyrkStages;
       const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * kSyrkRows;
       const int rows = (int)((K - r0 < kSyrkRows) ? (K - r0) : kSyrkRows);
+      double* dst = ring + (size_t)slot * kSyrkStageDoubles;
       if (lane == 0) {
         if (round > 0) {
           mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before async writes
         }
-        mbar_expect_tx(&full[slot], (uint32_t)(rows * kSyrkN * sizeof(double)));
+        if (use_map) {
+          // ONE tensor-map copy per chunk: a box of 64 rows x 132 columns of the K x 128 matrix -- the four columns
+          // past the matrix and the rows past K are zero-filled by the copy engine, so the box lands at the padded
+          // pitch and the last chunk needs no masking (the same trick as the GEMM's tiles)
+          mbar_expect_tx(&full[slot], (uint32_t)(kSyrkStageDoubles * sizeof(double)));
+          tma_load_2d(dst, &map, 0, (int)r0, &full[slot]);
+        } else {
+          mbar_expect_tx(&full[slot], (uint32_t)(rows * kSyrkN * sizeof(double)));
+        }
       }
       __syncwarp();
-      double* dst = ring + (size_t)slot * kSyrkStageDoubles;
-      for (int r = lane; r < rows; r += 32)
-        bulk_copy_g2s(dst + r * kSyrkPitch, A + (r0 + r) * kSyrkN, (uint32_t)(kSyrkN * sizeof(double)), &full[slot]);
+      if (!use_map) {      // no encoder: one bulk copy per row into the padded rows
+        for (int r = lane; r < rows; r += 32)
+          bulk_copy_g2s(dst + r * kSyrkPitch, A + (r0 + r) * kSyrkN, (uint32_t)(kSyrkN * sizeof(double)), &full[slot]);
+      }
     }
   } else {
     switch (warp) {
-      case 0: syrk_consumer<0>(ring, full, empty, K, my_chunks, lane); break;
-      case 1: syrk_consumer<1>(ring, full, empty, K, my_chunks, lane); break;
-      case 2: syrk_consumer<2>(ring, full, empty, K, my_chunks, lane); break;
-      case 3: syrk_consumer<3>(ring, full, empty, K, my_chunks, lane); break;
-      case 4: syrk_consumer<4>(ring, full, empty, K, my_chunks, lane); break;
-      case 5: syrk_consumer<5>(ring, full, empty, K, my_chunks, lane); break;
-      case 6: syrk_consumer<6>(ring, full, empty, K, my_chunks, lane); break;
-      default: syrk_consumer<7>(ring, full, empty, K, my_chunks, lane); break;
+      case 0: syrk_consumer<0>(ring, full, empty, K, my_chunks, lane, use_map != 0); break;
+      case 1: syrk_consumer<1>(ring, full, empty, K, my_chunks, lane, use_map != 0); break;
+      case 2: syrk_consumer<2>(ring, full, empty, K, my_chunks, lane, use_map != 0); break;
+      case 3: syrk_consumer<3>(ring, full, empty, K, my_chunks, lane, use_map != 0); break;
+      case 4: syrk_consumer<4>(ring, full, empty, K, my_chunks, lane, use_map != 0); break;
+      case 5: syrk_consumer<5>(ring, full, empty, K, my_chunks, lane, use_map != 0); break;
+      case 6: syrk_consumer<6>(ring, full, empty, K, my_chunks, lane, use_map != 0); break;
+      default: syrk_consumer<7>(ring, full, empty, K, my_chunks, lane, use_map != 0); break;
     }
   }
   __syncthreads();
@@ -1089,7 +1149,10 @@ int launch_syrk128(const double* A, int64_t K, const double* Cin, int64_t ldcin,
   if (grid > nchunks) grid = (int)nchunks;
   NUMS_NEED_WS((size_t)grid * kSyrkN * kSyrkN * sizeof(double), ws_bytes);
   NUMS_CUDA_OK(cudaFuncSetAttribute(dsyrk128_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dsyrk128_stream_kernel<<<grid, kSyrkThreads, smem, s>>>(A, K, static_cast<double*>(ws));
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const int use_map = encode_matrix_map(&map, A, K, kSyrkN, kSyrkN, kSyrkRows, kSyrkPitch) ? 1 : 0;
+  dsyrk128_stream_kernel<<<grid, kSyrkThreads, smem, s>>>(A, K, static_cast<double*>(ws), map, use_map);
   NUMS_LAUNCH_OK();
   return launch_fold_partials(static_cast<const double*>(ws), grid, kSyrkN, kSyrkN, Cin, ldcin, C, ldc, s);
 }

@@ -1,7 +1,11 @@
-# development aid: full GPU test-suite + ncu captures of the round-2 streaming kernels (one B200)
-python -m pytest tests -m gpu -x -q > gpurun_out/s7_pytest.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/s7_pytest.log
-for t in lr skinny gemvn; do
-  python scripts/ncu_target.py $t > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on --launch-skip 2 -c 1 -k regex:"lr_grad_hess_fano|skinny_dense|gemv_rows_f64" -o gpurun_out/r2_$t -f python scripts/ncu_target.py $t > gpurun_out/r2_ncu_$t.log 2>&1; echo ncu $t rc=$?
-done
-ls -la gpurun_out/r2_lr.ncu-rep gpurun_out/r2_skinny.ncu-rep gpurun_out/r2_gemvn.ncu-rep
-python scripts/gpu_probe.py lr 2>&1 | grep lr_fused
+# development aid: targeted GPU tests + probes (one B200)
+python -m pytest tests/test_gpu_parity.py -x -q -k "gram or qr or tensordot or newton" > gpurun_out/s10_pytest.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/s10_pytest.log
+python scripts/probe_gram.py; NUMS_SYRK_STREAM=0 python scripts/probe_gram.py
+python bench.py --steps 5 --warmup 3 --skip-cpu > gpurun_out/s10_bench_n1.json 2> gpurun_out/s10_bench_n1.err; echo bench rc=$?
+python - <<'PY'
+import json
+d=json.load(open("gpurun_out/s10_bench_n1.json"))
+print(d["value"], d["ms_per_step"])
+for k,v in d["workloads"].items(): print(" ",k,{a:b for a,b in v.items() if a in ("value","unit","ms","error")})
+PY
+python -c "import __graft_entry__ as g; g.smoke()"
