@@ -1157,6 +1157,117 @@ int launch_syrk128(const double* A, int64_t K, const double* Cin, int64_t ldcin,
   return launch_fold_partials(static_cast<const double*>(ws), grid, kSyrkN, kSyrkN, Cin, ldcin, C, ldc, s);
 }
 
+// --------------------------------------------------------------------------------------
+// Tall block times small square: C (M x 128) = A (M x 128, dense) . B (128 x 128, dense) -- the explicit Q of
+// TSQR, Q_i = X_i R^-1 (application.py:833-845; config 3: eight 2 097 152 x 128 blocks).  On the tiled GEMM every
+// 128 x 128 output tile has only four k-tiles to amortise its pipeline fill and its epilogue over (27 TFLOP/s).
+// Here B never moves: warp w keeps the 128 x 16 slab of B it multiplies with as 64 fragment registers per lane
+// for the whole kernel, a producer warp streams 64-row chunks of A through the same padded tensor-map ring as
+// the SYRK kernel above, every warp reads the whole chunk (conflict-free fragment reads at pitch 132) and writes
+// its 16 output columns straight from the accumulators.  Two LDS per four DMMAs, no CTA barrier, no tile
+// prologue: the kernel runs at the tensor pipe's rate.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSyrkThreads, 1)
+dgemm_tall128_stream_kernel(const double* __restrict__ B, double* __restrict__ C, int64_t M,
+                            const __grid_constant__ CUtensorMap map) {
+  extern __shared__ __align__(128) double tall_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* ring = tall_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)kSyrkStages * kSyrkStageDoubles);
+  uint64_t* empty = full + kSyrkStages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSyrkStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t nchunks = (M + kSyrkRows - 1) / kSyrkRows;
+  const int64_t my_chunks = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int64_t i = 0; i < my_chunks; ++i) {
+        const int slot = (int)(i % kSyrkStages);
+        const int64_t round = i / kSyrkStages;
+        if (round > 0) {
+          mbar_wait(&empty[slot], (uint32_t)((round - 1) & 1));
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads before async writes
+        }
+        const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * kSyrkRows;
+        mbar_expect_tx(&full[slot], (uint32_t)(kSyrkStageDoubles * sizeof(double)));
+        tma_load_2d(ring + (size_t)slot * kSyrkStageDoubles, &map, 0, (int)r0, &full[slot]);
+      }
+    }
+    return;
+  }
+  const int g = lane >> 2, t = lane & 3;
+  // this warp's slab of B as fragments: bf[ks][j] = B[4 ks + t][16 warp + 8 j + g]
+  double bf[kSyrkN / 4][2];
+#pragma unroll
+  for (int ks = 0; ks < kSyrkN / 4; ++ks)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) bf[ks][j] = B[(size_t)(4 * ks + t) * kSyrkN + 16 * warp + 8 * j + g];
+  for (int64_t i = 0; i < my_chunks; ++i) {
+    const int slot = (int)(i % kSyrkStages);
+    mbar_wait(&full[slot], (uint32_t)((i / kSyrkStages) & 1));
+    const int64_t r0 = ((int64_t)blockIdx.x + i * gridDim.x) * kSyrkRows;
+    const double* tile = ring + (size_t)slot * kSyrkStageDoubles;
+#pragma unroll 1
+    for (int rb = 0; rb < kSyrkRows / 8; rb += 2) {        // two 8-row blocks at a time: four independent accumulators
+      double acc[2][2][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[u][j][0] = acc[u][j][1] = 0.0;
+      const double* a0 = tile + (8 * rb + g) * kSyrkPitch + t;
+      const double* a1 = a0 + 8 * kSyrkPitch;
+#pragma unroll
+      for (int ks = 0; ks < kSyrkN / 4; ++ks) {
+        const double x0 = a0[4 * ks], x1 = a1[4 * ks];
+        dmma884(acc[0][0], x0, bf[ks][0]);
+        dmma884(acc[0][1], x0, bf[ks][1]);
+        dmma884(acc[1][0], x1, bf[ks][0]);
+        dmma884(acc[1][1], x1, bf[ks][1]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t row = r0 + 8 * (rb + u) + g;
+        if (row < M) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            __stcs(reinterpret_cast<double2*>(C + row * kSyrkN + 16 * warp + 8 * j + 2 * t),
+                   make_double2(acc[u][j][0], acc[u][j][1]));
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
+  }
+}
+
+inline bool tall128_stream_enabled() {   // NUMS_TALL_STREAM=0 sends X . R^-1 through the tiled GEMM (A/B measurements)
+  static const bool on = []() { const char* v = getenv("NUMS_TALL_STREAM"); return !(v && v[0] == '0'); }();
+  return on;
+}
+
+// Returns NUMS_OK with *handled = false when the tensor-map encoder is unavailable (the caller falls back).
+int launch_tall128(const double* A, const double* B, double* C, int64_t M, cudaStream_t s, bool* handled) {
+  *handled = false;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (!encode_matrix_map(&map, A, M, kSyrkN, kSyrkN, kSyrkRows, kSyrkPitch)) return NUMS_OK;
+  *handled = true;
+  const size_t smem = (size_t)kSyrkStages * kSyrkStageDoubles * sizeof(double) + 2 * kSyrkStages * sizeof(uint64_t);
+  const int64_t nchunks = (M + kSyrkRows - 1) / kSyrkRows;
+  int grid = sm_count();
+  if (grid > nchunks) grid = (int)nchunks;
+  NUMS_CUDA_OK(cudaFuncSetAttribute(dgemm_tall128_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dgemm_tall128_stream_kernel<<<grid, kSyrkThreads, smem, s>>>(B, C, M, map);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
+}
+
 template <int MB, int NB>
 int launch_skinny(const double* A, int64_t lda, const double* B, int64_t ldb, int M, int N, int64_t K,
                   const double* Cin, int64_t ldcin, double* C, int64_t ldc, void* ws, size_t ws_bytes,
@@ -1792,6 +1903,12 @@ int run_gemm_typed(int ta, int tb, int64_t M, int64_t N, int64_t K, const T* A, 
     if (aligned && ta && !tb && A == B && M == kSyrkN && N == kSyrkN && lda == kSyrkN && ldb == kSyrkN && K >= 16384
         && syrk_stream_enabled())
       return launch_syrk128(A, K, Cin, ldc, C, ldc, ws, ws_bytes, s);
+    if (aligned && !ta && !tb && N == kSyrkN && K == kSyrkN && lda == kSyrkN && ldb == kSyrkN && ldc == kSyrkN
+        && M >= 16384 && Cin == nullptr && (reinterpret_cast<uintptr_t>(C) & 15u) == 0 && tall128_stream_enabled()) {
+      bool handled = false;
+      const int rc = launch_tall128(A, B, C, M, s, &handled);
+      if (rc != NUMS_OK || handled) return rc;
+    }
     const bool worthwhile = M * N >= 32 * 32 || K >= 4096;
     if (aligned && worthwhile)
       return run_dgemm(ta, tb, M, N, K, A, lda, B, ldb, Cin, ldc, C, ldc, ws, ws_bytes, s);

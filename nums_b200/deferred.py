@@ -20,6 +20,7 @@ from nums_b200 import _lib, cuda_compute
 from nums_b200._lib import LIB
 
 MIN_EXTENT = 64   # smaller outputs / vector forms run eagerly (GEMV / split-K kernels)
+STREAM_MIN_ROWS = 16384   # (m x 128) . (128 x 128) with m at least this runs on dgemm_tall128_stream_kernel (gemm.cu)
 MAX_GROUPS = 16   # launches a flush may be cut into to overlap in-flight uploads (see _launch_groups)
 
 
@@ -111,6 +112,9 @@ class ContractionQueue(object):
         k2, n = int(a2_shape[0]), int(a2_shape[1])
         if k != k2 or m < MIN_EXTENT or n < MIN_EXTENT or k < 1:
             return None
+        if k == 128 and n == 128 and m >= STREAM_MIN_ROWS and not a1_T and not a2_T and a1.is_contiguous() \
+                and a2.is_contiguous():
+            return None       # tall block times small square (the Q of TSQR): the eager streaming kernel is faster
         x = cuda_compute._operand(a1, a1_shape, a1_T)     # metadata only: no kernel, no wait for uploads
         y = cuda_compute._operand(a2, a2_shape, a2_T)
         A, ta, lda = cuda_compute._as_matrix(x, m, k)

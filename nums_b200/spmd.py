@@ -973,7 +973,8 @@ class SpmdSystem(object):
         if op == "tensordot":
             if (axes == 1 and len(s1) == 2 and len(s2) == 2 and a1.lazy is None and a2.lazy is None
                     and a1.dtype == _F64 and a2.dtype == _F64 and s1[1] == s2[0]
-                    and s1[0] >= LAZY_MIN_EXTENT and s2[1] >= LAZY_MIN_EXTENT and s1[1] >= 1):
+                    and s1[0] >= LAZY_MIN_EXTENT and s2[1] >= LAZY_MIN_EXTENT and s1[1] >= 1
+                    and not (s1[1] == 128 and s2[1] == 128 and s1[0] >= 16384 and not t1 and not t2)):
                 hint = self._hint(sysk)
                 hint = 0 if hint is None else hint
                 item = ("dot", a1, a2, tuple(s1), tuple(s2), bool(t1), bool(t2), self._term_rank(a1, a2, hint))

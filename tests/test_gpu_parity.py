@@ -530,6 +530,17 @@ def test_gram_128_streaming_syrk(cuda_system, k):
     assert rel_fro(R * sg[:, None], Rref) <= 1e-10
 
 
+@pytest.mark.parametrize("m", [16384, 16384 + 41, 200_003])
+def test_tall_times_square_128_stream(cuda_system, oracle, m):
+    """(m x 128) . (128 x 128), the explicit Q of TSQR (application.py:833-845): streaming kernel with B resident in
+    registers; ragged last chunk; also through indirect_tsqr-like use with a transposed / non-dense operand (fallback)."""
+    rng = np.random.default_rng(m)
+    X = rng.standard_normal((m, 128))
+    Rinv = rng.standard_normal((128, 128))
+    _tdot(cuda_system, oracle, X, Rinv)
+    _tdot(cuda_system, oracle, X, np.ascontiguousarray(Rinv.T), b_T=True)        # not the streaming shape: tiled GEMM
+
+
 def test_tensordot_int_f32_nd(cuda_system, oracle):
     A = np.arange(6 * 7, dtype=np.int64).reshape(6, 7)       # test_bop.py:38-42 uses arange matrices
     B = np.arange(7 * 5, dtype=np.int64).reshape(7, 5)
