@@ -1,9 +1,5 @@
-# development aid: targeted GPU tests + bench (one B200)
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -x -q -k "gram or qr or tensordot or tall or tsqr or config3" > gpurun_out/s11_pytest.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/s11_pytest.log
-python bench.py --steps 5 --warmup 3 --skip-cpu > gpurun_out/s11_bench_n1.json 2> gpurun_out/s11_bench_n1.err; echo bench rc=$?
-python - <<'PY'
-import json
-d=json.load(open("gpurun_out/s11_bench_n1.json"))
-print(d["value"], d["ms_per_step"])
-for k,v in d["workloads"].items(): print(" ",k,{a:b for a,b in v.items() if a in ("value","unit","ms","error")})
-PY
+# development aid: ncu captures of the round-2 streaming kernels (one B200)
+for t in syrk tall; do
+  python scripts/ncu_target.py $t > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on --launch-skip 2 -c 1 -k regex:"dsyrk128|tall128" -o gpurun_out/r2_$t -f python scripts/ncu_target.py $t > gpurun_out/r2_ncu_$t.log 2>&1; echo ncu $t rc=$?
+done
+ls -la gpurun_out/r2_syrk.ncu-rep gpurun_out/r2_tall.ncu-rep

@@ -60,6 +60,15 @@ elif which == "gemvn":        # X beta (glms.py:140-143) on one config-4 block
     b = torch.randn((d,), dtype=torch.float64, device=dev)
     for _ in range(4):
         z = system.bop("tensordot", X, b, (n, d), (d,), False, False, axes=1, syskwargs={})
+elif which == "syrk":         # Gram matrix of one config-3 block (the TSQR leaf on the Gram path)
+    X = torch.randn((2_097_152, 128), dtype=torch.float64, device=dev)
+    for _ in range(4):
+        gmat = cc._gram_of(X)
+elif which == "tall":         # Q = X R^-1 of one config-3 block
+    X = torch.randn((2_097_152, 128), dtype=torch.float64, device=dev)
+    Rinv = torch.randn((128, 128), dtype=torch.float64, device=dev)
+    for _ in range(4):
+        qmat = cc.tensordot(X, Rinv, 1)
 elif which == "qr":
     X = torch.randn((262144, 128), dtype=torch.float64, device=dev)
     for _ in range(2):
