@@ -78,14 +78,14 @@ class CudaSystem(object):
             if name.startswith("_"):
                 continue
             self.remote_functions[name] = fn
-            self.methods[name] = self._make_callable(name)
+            self._publish(name, self._make_callable(name))
         if "bop" in self.remote_functions:
             self._bop_kernel = self.remote_functions["bop"]
-            self.methods["bop"] = self._call_bop          # the per-block hot call: a leaner copy of ``call``
+            self._publish("bop", self._call_bop)          # the per-block hot call: a leaner copy of ``call``
         # optional kernels beyond the 28 interface methods (fused logistic-regression step)
         for name, fn in getattr(self.compute_module, "EXTRA_KERNELS", {}).items():
             self.remote_functions[name] = fn
-            self.methods[name] = self._make_callable(name)
+            self._publish(name, self._make_callable(name))
 
     def shutdown(self):
         # like SerialSystem.shutdown (systems.py:91-92) this leaves the system usable: the reference keeps
@@ -97,6 +97,16 @@ class CudaSystem(object):
             return self.call(name, *args, **kwargs)
         kernel.__name__ = name
         return kernel
+
+    def _publish(self, name, fn):
+        """Make ``system.<name>`` resolve to ``fn``: in ``methods`` (where the reference's System looks,
+        systems.py:62-66) AND as an instance attribute, which shadows the abstract stub of the same name that
+        the reference's ``System`` inherits from ``ComputeInterface`` -- so that reference_compat's subclasses can
+        use the plain C attribute lookup instead of the reference's Python-level ``__getattribute__``."""
+        self.methods[name] = fn
+        owner = next((k for k in type(self).__mro__ if name in k.__dict__), None)
+        if owner is None or owner.__name__ == "ComputeInterface":      # never shadow the system's own API
+            self.__dict__[name] = fn
 
     def __getattr__(self, name):
         # only reached when normal lookup fails: kernel names are routed to ``call``
@@ -203,7 +213,7 @@ class CudaSystem(object):
             return
         device_fn = getattr(self.compute_module, "DEVICE_FUNCTIONS", {}).get(name)
         self.remote_functions[name] = device_fn if device_fn is not None else _host_function(func)
-        self.methods[name] = self._make_callable(name)
+        self._publish(name, self._make_callable(name))
 
     def nodes(self):
         return [{"Resources": {"node:%d" % r: 1.0}} for r in range(self.world_size)]

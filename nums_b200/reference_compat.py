@@ -210,7 +210,12 @@ def cuda_system_class():
         from nums_b200.cuda_system import CudaSystem
 
         class ReferenceCudaSystem(CudaSystem, SerialSystem):
-            pass
+            # The reference's System routes kernel names through a Python-level __getattribute__ (systems.py:62-66),
+            # which then intercepts EVERY attribute access of the system object (~1 us each, ~16 per kernel call
+            # inside our dispatch code).  CudaSystem resolves kernel names in __getattr__ instead -- reached only
+            # when normal lookup fails -- so plain lookups can take the C fast path again; no kernel name collides
+            # with an attribute of the class (tests/test_host_logic.py).
+            __getattribute__ = object.__getattribute__
 
         _system_cls = ReferenceCudaSystem
     return _system_cls
@@ -228,7 +233,7 @@ def spmd_system_class():
         from nums_b200.spmd import SpmdSystem
 
         class ReferenceSpmdSystem(SpmdSystem, SerialSystem):
-            pass
+            __getattribute__ = object.__getattribute__      # see ReferenceCudaSystem
 
         _spmd_cls = ReferenceSpmdSystem
     return _spmd_cls

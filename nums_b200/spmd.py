@@ -557,7 +557,7 @@ class SpmdSystem(object):
             names = [n for n in dir(self.local.imp) if not n.startswith("_") and callable(getattr(self.local.imp, n))]
         for name in names:
             self.remote_functions[name] = name
-            self.methods[name] = self._make_callable(name)
+            self._publish(name, self._make_callable(name))
         self.comm.setup_side_channel()
 
     def shutdown(self):
@@ -568,6 +568,13 @@ class SpmdSystem(object):
             return self.call(name, *args, **kwargs)
         kernel.__name__ = name
         return kernel
+
+    def _publish(self, name, fn):
+        """``system.<name>`` -> ``fn`` through ``methods`` and as an instance attribute (see CudaSystem._publish)."""
+        self.methods[name] = fn
+        owner = next((k for k in type(self).__mro__ if name in k.__dict__), None)
+        if owner is None or owner.__name__ == "ComputeInterface":      # never shadow the system's own API
+            self.__dict__[name] = fn
 
     def __getattr__(self, name):
         methods = self.__dict__.get("methods", {})
@@ -584,7 +591,7 @@ class SpmdSystem(object):
             return
         self.local.register(name, func, remote_params)
         self.remote_functions[name] = name
-        self.methods[name] = self._make_callable(name)
+        self._publish(name, self._make_callable(name))
         self._registered.add(name)
 
     def nodes(self):

@@ -57,3 +57,35 @@ def test_ravel_indices_numpy_semantics():
     for bad in [(4, 0, 0), (0, -6, 0), (0, 0, 6)]:
         with pytest.raises(IndexError):
             _ravel_indices([bad], shape)
+
+
+def test_reference_system_subclasses_route_kernel_names_without_the_slow_getattribute():
+    """reference_compat's system classes take object.__getattribute__ (the reference's Python-level override costs
+    ~1 us per attribute access): kernel names must still resolve (through __getattr__) and must not collide with
+    any real attribute of the classes."""
+    from nums_b200 import reference_compat
+    if not reference_compat.available():
+        pytest.skip("reference not present")
+    from oracle import np_oracle
+    from oracle.cpu_system import OracleSystem
+    cls = reference_compat.spmd_system_class()
+    assert cls.__getattribute__ is object.__getattribute__
+    assert reference_compat.cuda_system_class().__getattribute__ is object.__getattribute__
+    system = cls(OracleSystem(), check=True)
+    system.rng_cls = np_oracle.RNG
+    system.init()
+    from nums.core.systems.interfaces import ComputeInterface
+    import inspect
+    kernel_names = [n for n, _ in inspect.getmembers(ComputeInterface, predicate=inspect.isfunction)]
+    assert len(kernel_names) >= 28
+    # the reference's System inherits abstract stubs of the kernel names from ComputeInterface: the published
+    # instance attributes must shadow them, and nothing else of the class may carry a kernel's name
+    for klass in (cls, reference_compat.cuda_system_class()):
+        for name in kernel_names + ["lr_grad_hess", "newton_step", "read_csv_block", "write_block_fs"]:
+            owner = next((k for k in klass.__mro__ if name in k.__dict__), None)
+            assert owner is None or owner.__name__ == "ComputeInterface", (name, owner)
+    for name in kernel_names:
+        assert getattr(system, name) is system.methods[name], name
+    a = system.put(np.arange(6.0))
+    out = system.bop("add", a, a, (6,), (6,), False, False, axes=None, syskwargs={"grid_entry": (0,), "grid_shape": (1,)})
+    assert np.array_equal(system.get(out), 2 * np.arange(6.0))
