@@ -507,10 +507,9 @@ def sharded_workloads(system, comm, quick, out=None):
         vs = [torch.rand(n // G, dtype=torch.float64, device=dev) for _ in mine]
         shape = (n // G,)
 
-        def bop_add():
+        def bop_add():      # (cuda_time brackets the launches with events and waits for the end event itself)
             for u, v, i in zip(us, vs, mine):
                 system.bop("add", u, v, shape, shape, False, False, axes=None, syskwargs={"grid_entry": (i,), "grid_shape": (G,)})
-            torch.cuda.synchronize()
         t = timed(bop_add, 5 if quick else 20)
         out["bop_add"] = {"value": 24.0 * n / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
                           "workload": "float64 add of two 1e8-element arrays, 8 blocks dealt over %d GPU(s), no exchange" % world}
@@ -597,7 +596,7 @@ def api_workloads(host, quick, out=None):
         n = 100_000_000
         U = distributed((n,), (n // G,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
         V = distributed((n,), (n // G,), lambda s: torch.rand(s, dtype=torch.float64, device=dev))
-        t = timed(lambda: (host.launch(U + V), torch.cuda.synchronize()), 5 if quick else 20)
+        t = timed(lambda: host.launch(U + V), 5 if quick else 20)
         out["bop_add_api"] = {"value": 24.0 * n / t / 1e9, "unit": "GB/s", "ms": t * 1e3,
                               "workload": "BlockArray.__add__ of two 1e8-element float64 arrays, 8 blocks over %d GPU(s) through "
                                           "SpmdSystem (shard-local, no exchange)" % world}
@@ -888,11 +887,15 @@ def run_gpu(args):
 
         def step_e2e(reference_get=False):
             # puts are asynchronous (upload stream) and get() drains finished block rows while later ones
-            # compute.  Streaming order of the 128 puts: row 0 of A, then B column by column, then the other
-            # rows of A -- C(0, j) can start as soon as column j of B has landed, C(i, :) as soon as row i of A.
+            # compute.  Streaming order of the 128 puts: row 0 of A and column 0 of B (C(0, 0) can start), then
+            # alternately row i of A and column i of B -- every arrival completes the operands of an L-shaped
+            # front of 2 i + 1 result blocks, so the work available to the GEMM grows quadratically while the
+            # uploads proceed linearly and the tensor pipe never waits for PCIe after the first 16 blocks.
             a = blockarray_from_blocks(host, a_host, [(0, k) for k in range(GRID)])
-            b = blockarray_from_blocks(host, b_host, [(k, j) for j in range(GRID) for k in range(GRID)])
-            blockarray_from_blocks(host, a_host, [(i, k) for i in range(1, GRID) for k in range(GRID)], into=a)
+            b = blockarray_from_blocks(host, b_host, [(k, 0) for k in range(GRID)])
+            for i in range(1, GRID):
+                blockarray_from_blocks(host, a_host, [(i, k) for k in range(GRID)], into=a)
+                blockarray_from_blocks(host, b_host, [(k, i) for k in range(GRID)], into=b)
             c = a @ b
             return c.get() if reference_get else host.get(c)
         parallelism = ("1 GPU; host layers = %s; BlockArray.__matmul__ -> _tensordot issues 512 tensordot + 448 add kernel "

@@ -535,6 +535,7 @@ class SpmdSystem(object):
         self._next = 0
         self._bop_meta = {}
         self._infer_memo = {}
+        self._specials = {n[3:]: getattr(self, n) for n in dir(type(self)) if n.startswith("_k_")}   # kernel name -> handler
         self._owners = {}
         self._lazies = []
         self._scatters = []                   # weakrefs to handles whose value is a _LazyScatter
@@ -837,7 +838,7 @@ class SpmdSystem(object):
         if name == "touch":
             self.flush()
             return True
-        special = getattr(self, "_k_" + name, None)
+        special = self._specials.get(name)
         if special is not None:
             out = special(args, kwargs, sysk)
             if out is not _NOT_HANDLED:

@@ -1,5 +1,11 @@
-# development aid: ncu captures of the round-2 streaming kernels (one B200)
-for t in syrk tall; do
-  python scripts/ncu_target.py $t > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on --launch-skip 2 -c 1 -k regex:"dsyrk128|tall128" -o gpurun_out/r2_$t -f python scripts/ncu_target.py $t > gpurun_out/r2_ncu_$t.log 2>&1; echo ncu $t rc=$?
-done
-ls -la gpurun_out/r2_syrk.ncu-rep gpurun_out/r2_tall.ncu-rep
+# development aid: full GPU test-suite, bench, Newton path probe (one B200)
+python -m pytest tests -m gpu -x -q > gpurun_out/s12_pytest.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/s12_pytest.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/s12_bench_n1.json 2> gpurun_out/s12_bench_n1.err; echo bench rc=$?
+python - <<'PY'
+import json
+d=json.load(open("gpurun_out/s12_bench_n1.json"))
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"])
+for k,v in d["workloads"].items(): print(" ",k,{a:b for a,b in v.items() if a in ("value","unit","ms","error")})
+PY
+python scripts/probe_newton_path.py 2>/dev/null | head -1
+python -c "import __graft_entry__ as g; g.smoke()"
