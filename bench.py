@@ -887,15 +887,14 @@ def run_gpu(args):
 
         def step_e2e(reference_get=False):
             # puts are asynchronous (upload stream) and get() drains finished block rows while later ones
-            # compute.  Streaming order of the 128 puts: row 0 of A and column 0 of B (C(0, 0) can start), then
-            # alternately row i of A and column i of B -- every arrival completes the operands of an L-shaped
-            # front of 2 i + 1 result blocks, so the work available to the GEMM grows quadratically while the
-            # uploads proceed linearly and the tensor pipe never waits for PCIe after the first 16 blocks.
+            # compute.  Streaming order of the 128 puts: row 0 of A, then B column by column, then the other
+            # rows of A -- C(0, j) can start as soon as column j of B has landed, C(i, :) as soon as row i of A.
+            # (Measured alternative: row i of A / column i of B alternately, which feeds the GEMM in L-shaped fronts
+            # and never starves it -- but then no block ROW of C is complete before the very end, the drain of
+            # get_assembled cannot overlap the compute any more, and the step takes 306 ms instead of 272.)
             a = blockarray_from_blocks(host, a_host, [(0, k) for k in range(GRID)])
-            b = blockarray_from_blocks(host, b_host, [(k, 0) for k in range(GRID)])
-            for i in range(1, GRID):
-                blockarray_from_blocks(host, a_host, [(i, k) for k in range(GRID)], into=a)
-                blockarray_from_blocks(host, b_host, [(k, i) for k in range(GRID)], into=b)
+            b = blockarray_from_blocks(host, b_host, [(k, j) for j in range(GRID) for k in range(GRID)])
+            blockarray_from_blocks(host, a_host, [(i, k) for i in range(1, GRID) for k in range(GRID)], into=a)
             c = a @ b
             return c.get() if reference_get else host.get(c)
         parallelism = ("1 GPU; host layers = %s; BlockArray.__matmul__ -> _tensordot issues 512 tensordot + 448 add kernel "
