@@ -44,6 +44,7 @@ def newton(app, model, beta, X, y, tol, max_iter):
     if not _fusable(app, model, beta, X, y):
         return _reference_newton()(app, model, beta, X, y, tol, max_iter)
     system = app.system
+    methods = getattr(system, "methods", {})
     G, d = X.grid.grid_shape[0], X.shape[1]
     tol_value = float(np.asarray(tol.get() if hasattr(tol, "get") else tol))
     one = {"grid_entry": (0,), "grid_shape": (1,)}
@@ -57,10 +58,27 @@ def newton(app, model, beta, X, y, tol, max_iter):
             raise np.linalg.LinAlgError("Singular matrix")
         return gmax <= tol_value
 
+    # Row blocks that live on the same device go into ONE multi-block launch (up to 16 blocks each): group them by
+    # their home (SpmdSystem handles carry it; on a single GPU everything is one group).
+    groups = {}
+    for i in range(G):
+        groups.setdefault(getattr(X.blocks[i, 0].oid, "home", 0), []).append(i)
+    multi = "lr_grad_hess_multi" in methods and any(len(g) > 1 for g in groups.values())
     for _ in range(max_iter):
-        parts = [system.lr_grad_hess(X.blocks[i, 0].oid, y.blocks[i].oid, beta_oid,
-                                     syskwargs={"grid_entry": (i, 0), "grid_shape": (G, 1)}) for i in range(G)]
-        gh = parts[0] if G == 1 else system.sum_reduce(*parts, syskwargs=one)
+        if multi:
+            parts = []
+            for members in groups.values():
+                for lo in range(0, len(members), 16):
+                    chunk = members[lo:lo + 16]
+                    flat = []
+                    for i in chunk:
+                        flat.extend((X.blocks[i, 0].oid, y.blocks[i].oid))
+                    parts.append(system.lr_grad_hess_multi(*flat, beta_oid,
+                                                           syskwargs={"grid_entry": (chunk[0], 0), "grid_shape": (G, 1)}))
+        else:
+            parts = [system.lr_grad_hess(X.blocks[i, 0].oid, y.blocks[i].oid, beta_oid,
+                                         syskwargs={"grid_entry": (i, 0), "grid_shape": (G, 1)}) for i in range(G)]
+        gh = parts[0] if len(parts) == 1 else system.sum_reduce(*parts, syskwargs=one)
         beta_oid, status = system.newton_step(gh, beta_oid, syskwargs=one)
         # The convergence test of iteration i (glms.py:370) is read one iteration late: iteration i + 1 is already
         # enqueued when the host looks at the 16 status bytes of iteration i, so the device never idles on the

@@ -356,6 +356,9 @@ def infer_result(name, args, kwargs, meta_of):
         if name == "lr_grad_hess":
             d = int(meta_of(args[2])[0][0])
             return blk((d + d * d,), np.float64)
+        if name == "lr_grad_hess_multi":
+            d = int(meta_of(args[-1])[0][0])
+            return blk((d + d * d,), np.float64)
         if name == "newton_step":
             d = int(meta_of(args[1])[0][0])
             return ("t", [blk((d,), np.float64), blk((2,), np.float64)])
