@@ -472,38 +472,49 @@ lr_fold_kernel(const double* __restrict__ partial, int parts, int len, double* _
 // The 28 unordered group pairs (21 off-diagonal + 7 diagonal) are covered exactly once by the seven lines
 // {k, k+1, k+3} (mod 7) of the Fano plane -- every two points lie on exactly one line -- taking for line k
 // rows (G_k | G_{k+1}) and columns (G_k | G_{k+3}): blocks (k,k), (k,k+3), (k+1,k), (k+1,k+3).  That is the
-// minimum (28 blocks / 4 per product) and 30 % less tensor-pipe time than the triangular cover (measured: 0.613 ->
-// 0.587 ms on 11M x 28; DMMA shares the FP64 pipe with DFMA / DMUL, see DESIGN.md section 4 for what was tried next).  Operands: lane (g, t) of a warp holds row t, feature gi = g & 3 of
+// minimum (28 blocks / 4 per product) and 30 % less tensor-pipe time than the triangular cover (measured with the
+// round-1 structure: 0.613 -> 0.587 ms on 11M x 28; DMMA shares the FP64 pipe with DFMA / DMUL).  Operands: lane (g, t) of a warp holds row t, feature gi = g & 3 of
 // seven groups, loaded ROTATED by one group on the upper half of the warp (g >= 4), so that the A operand of
 // product k is register zv[k] on every lane; the B operand is s * zv[k] on the lower half and s * zv[(k+2) % 7]
 // on the upper half (seven selects).  No padding column is left for the gradient: g = X^T e is accumulated
 // next to it with seven FMAs per update (the plain FP64 pipe is otherwise idle).
 // ---------------------------------------------------------------------------------------------
-template <int ROWS, int STAGES>   // rows per tile (32, 24 or 16 per consumer warp) x ring depth
-__global__ void __launch_bounds__(kDenseThreads, 1)
-lr_grad_hess_fano28_kernel(const __grid_constant__ LrBlocks blk, const double* __restrict__ beta,
-                           double* __restrict__ partial) {
+// Structure: pass 1 of a tile (x . beta, sigmoid, one row per lane) simply precedes its pass 2 inside a warp, and the
+// latency chains of pass 1 are hidden by OTHER warps' tensor-pipe work -- thread-level parallelism instead of the
+// software pipelining of the round-1 kernel (pass 1 of tile i + 1 interleaved with pass 2 of tile i), which measured
+// slower (0.605 vs 0.577 ms with the same eight warps).  CW consumer warps of 32 rows each; every scheduler has its
+// own FP64 pipe, so CW must be a multiple of four or the tile time is set by the schedulers that got one warp more
+// (nine or ten consumer warps measured SLOWER than eight).  Twelve consumer warps -- three per scheduler, the most that
+// leaves 168 registers per thread -- leave no room for a producer warp (a 13th warp would cap every thread at 128
+// registers), so with INWARP lane 0 of warp 0 feeds the ring between its tiles: before tile i it waits until all
+// warps have handed back the slot of tile i - 1 and refills it with tile i - 1 + STAGES.  Tiles of CW x 32 rows,
+// STAGES-deep ring; a consumer needs only its current tile.  Measured on 11 M x 28: <12, 2, in-warp> 0.536 ms,
+// <11, 2, producer warp> 0.558, <8, 3, producer warp> 0.577 (profiles/r2_lr_kernel_experiments.md).
+template <int CW, int STAGES, bool INWARP>   // INWARP: no producer warp, lane 0 of warp 0 feeds the ring between its tiles
+__global__ void __launch_bounds__(32 * (CW + (INWARP ? 0 : 1)), 1)
+lr_grad_hess_fano28_tlp_kernel(const __grid_constant__ LrBlocks blk, const double* __restrict__ beta,
+                               double* __restrict__ partial) {
   constexpr int d = 28;
   constexpr int NG = 7;
-  constexpr int RW = ROWS / 8;          // rows of a tile handled by one consumer warp (one per lane in pass 1)
-  constexpr int GROUPS = RW / 4;        // rank-4 updates per warp and tile
+  constexpr int ROWS = 32 * CW;
+  constexpr int THREADS = 32 * (CW + (INWARP ? 0 : 1));
   extern __shared__ __align__(128) unsigned char lr_smem[];
   constexpr int tile_doubles = ROWS * d;
-  double* ring = reinterpret_cast<double*>(lr_smem);                       // STAGES tiles
-  double* scratch = ring + (size_t)STAGES * tile_doubles;            // 8 warps x 2 buffers x (32 s + 32 e)
-  double* bsm = scratch + 8 * 128;                                          // beta (32 doubles reserved)
+  double* ring = reinterpret_cast<double*>(lr_smem);
+  double* scratch = ring + (size_t)STAGES * tile_doubles;                   // CW warps x (32 s + 32 e)
+  double* bsm = scratch + CW * 64;
   uint64_t* full = reinterpret_cast<uint64_t*>(bsm + 32);
   uint64_t* empty = full + STAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int half = g >> 2, gi = g & 3;
 
-  for (int i = threadIdx.x; i < STAGES * tile_doubles; i += kDenseThreads) ring[i] = 0.0;
-  for (int i = threadIdx.x; i < 32; i += kDenseThreads) bsm[i] = i < d ? beta[i] : 0.0;
+  for (int i = threadIdx.x; i < STAGES * tile_doubles; i += THREADS) ring[i] = 0.0;
+  for (int i = threadIdx.x; i < 32; i += THREADS) bsm[i] = i < d ? beta[i] : 0.0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 8);
+      mbar_init(&empty[s], CW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -518,7 +529,20 @@ lr_grad_hess_fano28_kernel(const __grid_constant__ LrBlocks blk, const double* _
 #pragma unroll
   for (int k = 0; k < NG; ++k) hacc[k][0] = hacc[k][1] = gacc[k] = 0.0;
 
-  if (warp == 8) {
+  auto issue_tile = [&](int64_t i) {      // one bulk copy: tile i of this CTA into slot i % STAGES
+    const int slot = (int)(i % STAGES);
+    const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
+    const int b = lr_find_block(blk, tile);
+    const int64_t r0 = (tile - blk.tile_begin[b]) * ROWS;
+    const int64_t rows = (blk.rows[b] - r0 < ROWS) ? (blk.rows[b] - r0) : ROWS;
+    const uint32_t bytes = (uint32_t)(rows * d * sizeof(double));
+    mbar_expect_tx(&full[slot], bytes);
+    bulk_copy_g2s(ring + (size_t)slot * tile_doubles, blk.X[b] + r0 * d, bytes, &full[slot]);
+  };
+  if (INWARP && threadIdx.x == 0) {
+    for (int64_t i = 0; i < STAGES && i < my_tiles; ++i) issue_tile(i);
+  }
+  if (!INWARP && warp == CW) {
     if (lane == 0) {
       for (int64_t i = 0; i < my_tiles; ++i) {
         const int slot = (int)(i % STAGES);
@@ -535,60 +559,54 @@ lr_grad_hess_fano28_kernel(const __grid_constant__ LrBlocks blk, const double* _
       }
     }
   } else {
-    double* scr = scratch + warp * 128;
-    // feature offset of the j-th loaded value: group (j + half) mod 7, feature gi of it
+    double* scr_s = scratch + warp * 64;
+    double* scr_e = scr_s + 32;
     int zo[NG];
 #pragma unroll
     for (int j = 0; j < NG; ++j) zo[j] = 4 * ((j + half) % NG) + gi;
-    auto fetch_y = [&](int64_t tile, bool& valid) -> double {
-      const int b = lr_find_block(blk, tile);
-      const int64_t row = (tile - blk.tile_begin[b]) * ROWS + warp * RW + lane;
-      valid = lane < RW && row < blk.rows[b];
-      return valid ? blk.y[b][row] : 0.0;
-    };
-    auto dot_slice = [&](const double* xr, int q, double (&z)[4]) {   // features [4q, 4q + 4) of this lane's row
-      const int j = 4 * q;
-      const double2 v = *reinterpret_cast<const double2*>(xr + j);
-      const double2 w = *reinterpret_cast<const double2*>(xr + j + 2);
-      z[0] = fma(v.x, bsm[j], z[0]);
-      z[1] = fma(v.y, bsm[j + 1], z[1]);
-      z[2] = fma(w.x, bsm[j + 2], z[2]);
-      z[3] = fma(w.y, bsm[j + 3], z[3]);
-    };
-    auto finish = [&](const double (&z)[4], double yv, bool valid, double* out_s, double* out_e) {
-      const double mu = 1.0 / (1.0 + exp(-((z[0] + z[1]) + (z[2] + z[3]))));
-      out_s[lane] = valid ? mu * (1.0 - mu) : 0.0;
-      out_e[lane] = valid ? mu - yv : 0.0;
-    };
-
-    if (my_tiles > 0) {
-      bool valid0 = false;
-      const double y0 = fetch_y(blockIdx.x, valid0);
-      mbar_wait(&full[0], 0u);
-      double z[4] = {0.0, 0.0, 0.0, 0.0};
-      const double* xr = ring + (size_t)warp * RW * d + (lane < RW ? lane : 0) * d;
-#pragma unroll
-      for (int q = 0; q < NG; ++q) dot_slice(xr, q, z);
-      finish(z, y0, valid0, scr, scr + 32);
-      __syncwarp();
-    }
+    const int swz = (lane >> 2) & 1;           // chunk order c ^ swz: conflict-free 128-bit reads at a 224-byte row stride
     for (int64_t i = 0; i < my_tiles; ++i) {
       const int slot = (int)(i % STAGES);
-      const bool has_next = i + 1 < my_tiles;
-      const int nslot = has_next ? (int)((i + 1) % STAGES) : slot;
-      bool valid_next = false;
-      const double y_next = has_next ? fetch_y((int64_t)blockIdx.x + (i + 1) * gridDim.x, valid_next) : 0.0;
-      if (has_next) mbar_wait(&full[nslot], (uint32_t)(((i + 1) / STAGES) & 1));
-      const double* xs = ring + (size_t)slot * tile_doubles + (size_t)warp * RW * d;
-      const double* xr_next = ring + (size_t)nslot * tile_doubles + (size_t)warp * RW * d + (lane < RW ? lane : 0) * d;
-      const double* cur_s = scr + (i & 1) * 64;
-      const double* cur_e = cur_s + 32;
-      double* nxt_s = scr + ((i + 1) & 1) * 64;
-      double z[4] = {0.0, 0.0, 0.0, 0.0};
+      if (INWARP && warp == 0 && i >= 1) {
+        // the slot of tile i - 1 is refilled with tile i - 1 + STAGES as soon as all warps have handed it back
+        const int64_t nxt = i - 1 + STAGES;
+        if (lane == 0 && nxt < my_tiles) {
+          mbar_wait(&empty[(i - 1) % STAGES], (uint32_t)(((i - 1) / STAGES) & 1));
+          fence_proxy_async();
+          issue_tile(nxt);
+        }
+        __syncwarp();
+      }
+      const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
+      const int b = lr_find_block(blk, tile);
+      const int64_t row = (tile - blk.tile_begin[b]) * ROWS + warp * 32 + lane;
+      const bool valid = row < blk.rows[b];
+      const double yv = valid ? blk.y[b][row] : 0.0;
+      mbar_wait(&full[slot], (uint32_t)((i / STAGES) & 1));
+      const double* xs = ring + (size_t)slot * tile_doubles + (size_t)warp * 32 * d;
+      {   // pass 1: lane l owns row l of the warp's 32 rows
+        const double* xrow = xs + lane * d;
+        double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
 #pragma unroll
-      for (int q = 0; q < GROUPS; ++q) {
-        const double sv = cur_s[4 * q + t];
-        const double ev = cur_e[4 * q + t];
+        for (int c = 0; c < d / 2; c += 2) {
+          const double2 x0 = *reinterpret_cast<const double2*>(xrow + 2 * (c ^ swz));
+          const double2 x1 = *reinterpret_cast<const double2*>(xrow + 2 * ((c + 1) ^ swz));
+          const double2 b0 = *reinterpret_cast<const double2*>(bsm + 2 * (c ^ swz));
+          const double2 b1 = *reinterpret_cast<const double2*>(bsm + 2 * ((c + 1) ^ swz));
+          z0 = fma(x0.x, b0.x, z0);
+          z1 = fma(x0.y, b0.y, z1);
+          z2 = fma(x1.x, b1.x, z2);
+          z3 = fma(x1.y, b1.y, z3);
+        }
+        const double mu = 1.0 / (1.0 + exp(-((z0 + z1) + (z2 + z3))));
+        scr_s[lane] = valid ? mu * (1.0 - mu) : 0.0;   // rows past the end may hold stale data: weight 0
+        scr_e[lane] = valid ? mu - yv : 0.0;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {   // pass 2: H += x (s x)^T, seven DMMAs per rank-4 update; g += e x
+        const double sv = scr_s[4 * q + t];
+        const double ev = scr_e[4 * q + t];
         const double* xr = xs + (4 * q + t) * d;
         double zv[NG], sz[NG];
 #pragma unroll
@@ -598,34 +616,28 @@ lr_grad_hess_fano28_kernel(const __grid_constant__ LrBlocks blk, const double* _
           sz[j] = sv * zv[j];
           gacc[j] = fma(ev, zv[j], gacc[j]);
         }
-        // pass 1 of the next tile, spread over the updates (7 slices over GROUPS updates)
-#pragma unroll
-        for (int sl = (q * NG) / GROUPS; sl < ((q + 1) * NG) / GROUPS; ++sl) dot_slice(xr_next, sl, z);
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
           const double bk = half ? sz[(k + 2) % NG] : sz[k];
           dmma884(hacc[k], zv[k], bk);
         }
       }
-      finish(z, y_next, valid_next && has_next, nxt_s, nxt_s + 32);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[slot]);
     }
   }
   __syncthreads();
 
-  // ---- CTA fold: every warp lays its gradient and its covered Hessian blocks into an image of
-  //      d + d*d doubles; the output loop picks, for every (r, c), the position that was computed.
   constexpr int PER_WARP = d + d * d;
-  double* red = ring;          // 8 x 812 doubles = 52 KB <= the ring
-  if (warp < 8) {
+  double* red = ring;          // CW x 812 doubles <= the ring
+  if (warp < CW) {
     double* mine = red + warp * PER_WARP;
 #pragma unroll
     for (int j = 0; j < NG; ++j) {
       double v = gacc[j];
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (t == 0 && half == 0) mine[4 * j + gi] = v;       // (the upper half holds the same sums, rotated)
+      if (t == 0 && half == 0) mine[4 * j + gi] = v;
     }
 #pragma unroll
     for (int k = 0; k < NG; ++k) {
@@ -640,21 +652,44 @@ lr_grad_hess_fano28_kernel(const __grid_constant__ LrBlocks blk, const double* _
   }
   __syncthreads();
   double* out = partial + (size_t)blockIdx.x * PER_WARP;
-  for (int i = threadIdx.x; i < PER_WARP; i += kDenseThreads) {
+  for (int i = threadIdx.x; i < PER_WARP; i += THREADS) {
     int src = i;
     if (i >= d) {
       const int r = (i - d) / d, c = (i - d) - r * d;
       const int diff = (c / 4 - r / 4 + NG) % NG;
-      // computed orientations: column group - row group = 2, 3 or 6 (mod 7); the diagonal blocks are
-      // computed in full and read on their upper triangle, so H comes out exactly symmetric
       const bool as_is = diff == 0 ? r <= c : (diff == 2 || diff == 3 || diff == 6);
       src = as_is ? d + r * d + c : d + c * d + r;
     }
     double acc = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) acc += red[w * PER_WARP + src];
+    for (int w = 0; w < CW; ++w) acc += red[w * PER_WARP + src];
     out[i] = acc;
   }
+}
+
+template <int CW, int STAGES, bool INWARP>
+int launch_lr_fano28_tlp(LrBlocks blk, const double* beta, double* out, void* ws, size_t ws_bytes, cudaStream_t s) {
+  constexpr int d = 28, ROWS = 32 * CW;
+  int64_t tiles = 0;      // the block table arrives with tile counts for kTileRows-row tiles: recount
+  for (int b = 0; b < blk.count; ++b) {
+    blk.tile_begin[b] = tiles;
+    tiles += (blk.rows[b] + ROWS - 1) / ROWS;
+  }
+  blk.tile_begin[blk.count] = tiles;
+  const size_t tile_bytes = (size_t)ROWS * d * sizeof(double);
+  const size_t smem = STAGES * tile_bytes + (CW * 64 + 32) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+  const int len = d + d * d;
+  int grid = sm_count();
+  if (grid > tiles) grid = (int)tiles;
+  if (grid < 1) grid = 1;
+  NUMS_NEED_WS((size_t)grid * len * sizeof(double), ws_bytes);
+  NUMS_CUDA_OK(cudaFuncSetAttribute(lr_grad_hess_fano28_tlp_kernel<CW, STAGES, INWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  lr_grad_hess_fano28_tlp_kernel<CW, STAGES, INWARP><<<grid, 32 * (CW + (INWARP ? 0 : 1)), smem, s>>>(blk, beta, static_cast<double*>(ws));
+  NUMS_LAUNCH_OK();
+  lr_fold_kernel<<<(len + 7) / 8, 256, 0, s>>>(static_cast<const double*>(ws), grid, len, out);
+  NUMS_LAUNCH_OK();
+  return NUMS_OK;
 }
 
 inline bool lr_fano_enabled() {    // NUMS_LR_FANO=0 selects the triangular cover (A/B measurements)
@@ -662,40 +697,12 @@ inline bool lr_fano_enabled() {    // NUMS_LR_FANO=0 selects the triangular cove
   return on;
 }
 
-template <int ROWS, int STAGES>
-int launch_lr_fano28_variant(LrBlocks blk, const double* beta, double* out, void* ws, size_t ws_bytes, cudaStream_t s) {
-  constexpr int d = 28;
-  // the block table arrives with tile counts for kTileRows-row tiles: recount for this tile height
-  int64_t tiles = 0;
-  for (int b = 0; b < blk.count; ++b) {
-    blk.tile_begin[b] = tiles;
-    tiles += (blk.rows[b] + ROWS - 1) / ROWS;
-  }
-  blk.tile_begin[blk.count] = tiles;
-  const size_t tile_bytes = (size_t)ROWS * d * sizeof(double);
-  const size_t smem = STAGES * tile_bytes + (8 * 128 + 32) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
-  const int len = d + d * d;
-  int grid = sm_count();
-  if (grid > tiles) grid = (int)tiles;
-  if (grid < 1) grid = 1;
-  NUMS_NEED_WS((size_t)grid * len * sizeof(double), ws_bytes);
-  NUMS_CUDA_OK(cudaFuncSetAttribute(lr_grad_hess_fano28_kernel<ROWS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-  lr_grad_hess_fano28_kernel<ROWS, STAGES><<<grid, kDenseThreads, smem, s>>>(blk, beta, static_cast<double*>(ws));
-  NUMS_LAUNCH_OK();
-  lr_fold_kernel<<<(len + 7) / 8, 256, 0, s>>>(static_cast<const double*>(ws), grid, len, out);
-  NUMS_LAUNCH_OK();
-  return NUMS_OK;
-}
-
 int launch_lr_fano28(const LrBlocks& blk, const double* beta, double* out, void* ws, size_t ws_bytes, cudaStream_t s) {
-  static const int variant = []() { const char* v = getenv("NUMS_LR_TILE"); return v ? atoi(v) : 256; }();
-  switch (variant) {
-    // measured on 11M x 28 (profiles/r2_lr_kernel_experiments.md): 256 x 3: 0.59-0.60 ms, 192 x 5: 0.63, 128 x 7: 0.75 --
-    // the per-tile cost of pass 1 (one row per lane: only RW of 32 lanes busy) outweighs the deeper ring
-    case 192: return launch_lr_fano28_variant<192, 5>(blk, beta, out, ws, ws_bytes, s);
-    case 128: return launch_lr_fano28_variant<128, 7>(blk, beta, out, ws, ws_bytes, s);
-    default: return launch_lr_fano28_variant<256, 3>(blk, beta, out, ws, ws_bytes, s);
+  static const int variant = []() { const char* v = getenv("NUMS_LR_TILE"); return v ? atoi(v) : 1202; }();
+  switch (variant) {      // NUMS_LR_TILE = <consumer warps><stages, 2 digits>: A/B measurements
+    case 1102: return launch_lr_fano28_tlp<11, 2, false>(blk, beta, out, ws, ws_bytes, s);
+    case 803: return launch_lr_fano28_tlp<8, 3, false>(blk, beta, out, ws, ws_bytes, s);
+    default: return launch_lr_fano28_tlp<12, 2, true>(blk, beta, out, ws, ws_bytes, s);
   }
 }
 
