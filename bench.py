@@ -610,6 +610,10 @@ def api_workloads(host, quick, out=None):
                              "workload": "ArrayApplication.indirect_tsr on 16777216 x 128 float64, 8 row blocks over %d GPU(s): "
                                          "per-block Gram matrices summed on their owners, one all-reduce, one factorization "
                                          "(Householder tree over the ranks when the condition bound refuses), R replicated" % world}
+        t = timed(lambda: (host.launch(app.indirect_tsqr(X)[0]), torch.cuda.synchronize()), 2 if quick else 3)
+        out["tsqr_qr_api"] = {"value": (flops_r + 2.0 * m * ncol ** 2) / t / 1e12, "unit": "TFLOP/s", "ms": t * 1e3,
+                              "workload": "ArrayApplication.indirect_tsqr (Q = X R^-1 on every block's owner, R replicated) on "
+                                          "16777216 x 128 float64, 8 row blocks over %d GPU(s)" % world}
 
     def cfg4():
         N, d = 11_000_000, 28
