@@ -952,7 +952,11 @@ QR_GRAM_MIN_ASPECT = 8        # m >= 8 n
 QR_GRAM_MAX_COLS = 256
 QR_GRAM_ACCEPT_KAPPA = 30.0   # one Cholesky pass: error ~ kappa^2 eps  (< 1e-12)
 QR_GRAM_REFINE_KAPPA = 1.0e6  # two passes (CholeskyQR2) are as good as Householder below ~1e7
-QR_STATS = {"gram": 0, "gram2": 0, "householder": 0, "gram_fused": 0}
+QR_SHIFT_PLAIN_KAPPA = 1.0e7  # inside the shifted iteration a pass without shift is taken up to this bound
+QR_SHIFT_MAX_SHIFTS = 3       # shifted passes before the Householder kernel takes over
+QR_STATS = {"gram": 0, "gram2": 0, "gram3": 0, "householder": 0, "gram_fused": 0}
+# NUMS_QR_SHIFTED=0: ill-conditioned tall blocks go straight to the Householder kernel
+QR_SHIFTED_ENABLED = __import__("os").environ.get("NUMS_QR_SHIFTED", "1") != "0"
 # NUMS_QR_DEFER=0: qr(block, mode="r") factors at once instead of handing out a DeferredR
 QR_DEFER_ENABLED = __import__("os").environ.get("NUMS_QR_DEFER", "1") != "0"
 # NUMS_QR_GRAM=0 sends every block through the Householder kernel (measurements, paranoia)
@@ -1101,8 +1105,10 @@ def qr_r_ex(arr, gram=None):
     """(R, kappa_bound).  R is the k x n (k = min(m, n)) triangular factor of a 2-D block.
 
     Tall float64 blocks go through the Gram matrix: R = chol(A^T A)^T when the condition bound is
-    tiny, CholeskyQR2 when it is moderate; everything else (wide, short, ill-conditioned, f32) uses
-    the streaming Householder TSQR kernel (nums_qr), which is backward stable for any input."""
+    tiny, CholeskyQR2 when it is moderate, iterated shifted Cholesky passes when it is large or the Gram
+    matrix is not numerically positive definite (_shifted_cholesky_r); everything else (wide, short, f32,
+    exact zeros, more than 128 columns) uses the blocked Householder TSQR kernel (nums_qr), which is
+    backward stable for any input."""
     if arr.dim() != 2:
         raise ValueError("qr needs a 2-D block")
     if arr.dtype not in (torch.float64, torch.float32):
@@ -1112,21 +1118,92 @@ def qr_r_ex(arr, gram=None):
     m, n = arr.shape
     if gram is None and not _gram_path_ok(arr):
         return _householder_r(arr), None
-    low, low_inv, upper, kappa = _factor_gram(gram if gram is not None else _gram_of(arr))
+    g0 = gram if gram is not None else _gram_of(arr)
+    low, low_inv, upper, kappa = _factor_gram(g0)
     if kappa <= QR_GRAM_ACCEPT_KAPPA:
         QR_STATS["gram"] += 1
         return upper, kappa
     if kappa <= QR_GRAM_REFINE_KAPPA:
         # CholeskyQR2: Q1 = A L^-T, second Gram factor, R = (L1 L2)^T
         q1 = _empty((m, n), np.float64)
-        gemm_into(q1, arr, False, n, low_inv, True, n, m, n, n)
+        gemm_into(q1, arr, False, n, _materialize(_transpose_view(low_inv)), False, n, m, n, n)
         low2, _low2_inv, _upper2, kappa2 = _gram_factor(q1)
         if kappa2 <= QR_GRAM_ACCEPT_KAPPA:
             prod = _empty((n, n), np.float64)
             gemm_into(prod, low, False, n, low2, False, n, n, n, n)
             QR_STATS["gram2"] += 1
             return _materialize(_transpose_view(prod)), kappa
+    if QR_SHIFTED_ENABLED and n <= GRAM_FACTOR_FUSED_MAX:
+        r = _shifted_cholesky_r(arr, g0)
+        if r is not None:
+            QR_STATS["gram3"] += 1
+            return r, kappa
     return _householder_r(arr), kappa
+
+
+def _shifted_cholesky_r(arr, gram):
+    """R of an ill-conditioned tall float64 block by repeated (shifted) Cholesky passes on the streaming kernels
+    -- shifted CholeskyQR3 (Fukaya, Kannan, Nakatsukasa, Yamamoto, Yanagisawa, SIAM J. Sci. Comput. 2020),
+    iterated: with Q_0 = A and R = I, every pass factors the Gram matrix G of the current Q_i; while the bound on
+    cond_2(Q_i) is above QR_SHIFT_PLAIN_KAPPA (or G is not numerically positive definite) the factor is taken from
+    G + s I, s a small multiple of u trace(G) (see below), which is positive definite and lowers the condition number
+    by ~sqrt(s / |Q_i|^2) ~ 1e5 per pass; then Q_{i+1} = Q_i R_i^-1, R <- R_i R, until one plain
+    pass with a bound <= QR_GRAM_ACCEPT_KAPPA closes the iteration.  The result satisfies R^T R = A^T A and agrees
+    with LAPACK's Householder R to ~1e-14 for condition numbers up to 1e16 (oracle/shifted_cholqr_study.py); every
+    pass is one streaming SYRK, one 128-column triangular solve as a GEMM, one small factorization and one 40-byte
+    read-back.  Returns None when QR_SHIFT_MAX_SHIFTS shifted passes were not enough (exact zeros: the Householder
+    kernel takes over)."""
+    m, n = arr.shape
+    u = 2.0 ** -53
+    shift_rel = 11.0 * (float(m) * n + n * (n + 1.0)) * u
+    cur, r_acc, shifts = arr, None, 0
+    for _ in range(QR_SHIFT_MAX_SHIFTS + 3):
+        g = gram if gram is not None else _gram_of(cur)
+        gram = None
+        low, low_inv, upper, kappa = _factor_gram(g)
+        if kappa <= QR_GRAM_ACCEPT_KAPPA:
+            return upper if r_acc is None else _small_matmul(upper, r_acc)
+        if kappa > QR_SHIFT_PLAIN_KAPPA:
+            if shifts >= QR_SHIFT_MAX_SHIFTS:
+                return None
+            shifts += 1
+            dg = _materialize(g.as_strided((n,), (n + 1,)))             # trace(G): diagonal + sum, one 8-byte read-back
+            tr = _empty((), np.float64)
+            LIB.call_ws(LIB.dll.nums_reduce, g.device,
+                        ((_lib.REDUCE_CODE["sum"], dg.data_ptr(), _lib.F64, 1, n, 1, tr.data_ptr(), _lib.F64), (_stream(),)))
+            trace = float(tr.cpu().item())
+            if not np.isfinite(trace) or trace <= 0.0:
+                return None
+            # The theoretical shift 11 (m n + n (n + 1)) u |A|^2 guarantees that Cholesky runs to completion whatever
+            # the rounding errors of the Gram matrix were, but it grows with m and lowers the condition number by
+            # only sqrt(1 / shift) per pass (1.7e3 at m = 2 M).  Start at 11 n (n + 1) u trace(G) -- enough in every
+            # case of the study -- and escalate by factors of 100 up to the theoretical value when the factorization
+            # still breaks down (a retry costs one 0.3 ms small-matrix kernel, not a pass over the block).
+            kappa_s = float("inf")
+            c = min(11.0 * n * (n + 1.0) * u, shift_rel)
+            while True:
+                shift = _empty((n, n), np.float64)
+                LIB.check(LIB.dll.nums_fill(describe(shift), 0.0, _stream()))
+                LIB.check(LIB.dll.nums_fill(describe(shift.as_strided((n,), (n + 1,))), c * trace, _stream()))
+                low, low_inv, upper, kappa_s = _factor_gram(elementwise("add", g, shift))
+                if np.isfinite(kappa_s) or c >= shift_rel:
+                    break
+                c = min(c * 100.0, shift_rel)
+            if not np.isfinite(kappa_s):
+                return None
+        r_inv = _materialize(_transpose_view(low_inv))                  # R_i^-1 = (L^-1)^T, dense for the streaming GEMM
+        nxt = _empty((m, n), np.float64)
+        gemm_into(nxt, cur, False, n, r_inv, False, n, m, n, n)
+        cur = nxt
+        r_acc = upper if r_acc is None else _small_matmul(upper, r_acc)
+    return None
+
+
+def _small_matmul(a, b):
+    n = a.shape[0]
+    out = _empty((n, b.shape[1]), np.float64)
+    gemm_into(out, a, False, a.shape[1], b, False, b.shape[1], n, b.shape[1], a.shape[1])
+    return out
 
 
 def qr_r(arr):

@@ -878,12 +878,12 @@ def _qr_r_checks(cuda_system, X, r_tol, gram_tol):
 
 
 @pytest.mark.parametrize("kappa,branch,r_tol", [(1e0, "gram", 1e-10), (2e1, "gram2", 1e-10), (1e2, "gram2", 1e-10),
-                                               (1e5, "gram2", 1e-10), (1e9, "householder", None),
-                                               (1e13, "householder", None)])
+                                               (1e5, "gram2", 1e-10), (1e9, "gram3", 1e-10),
+                                               (1e13, "gram3", 1e-10)])
 def test_qr_graded_spectrum_branches(cuda_system, kappa, branch, r_tol):
-    """Tall float64 blocks of growing condition number: the 1e-10 sign-canonical bar on R must hold wherever
-    it is meaningful (two backward-stable factorizations agree to ~kappa * eps only), backward stability must
-    hold everywhere, and the branch the condition bound selects is the expected one."""
+    """Tall float64 blocks of growing condition number: the 1e-10 sign-canonical bar on R against LAPACK's
+    Householder R, backward stability (R^T R = X^T X), and the branch the condition bound selects: one Cholesky
+    pass, CholeskyQR2, iterated shifted Cholesky passes ("gram3", oracle/shifted_cholqr_study.py)."""
     X = _graded(40_000, 64, kappa, seed=int(np.log10(kappa)) + 7)
     ran = _qr_r_checks(cuda_system, X, r_tol, gram_tol=1e-13)
     assert ran[branch] == 1 and sum(ran.values()) == 1, ran
@@ -900,7 +900,18 @@ def test_qr_rank_deficient_and_float32(cuda_system):
     X[:, 7] = X[:, 3]                        # exactly rank deficient: the Gram matrix is not positive definite
     X[:, 20] = 0.5 * X[:, 1] - 2.0 * X[:, 2]
     ran = _qr_r_checks(cuda_system, X, None, gram_tol=1e-13)
-    assert ran["householder"] == 1 and ran["gram"] == 0 and ran["gram2"] == 0, ran
+    assert ran["gram3"] + ran["householder"] == 1 and ran["gram"] == 0 and ran["gram2"] == 0, ran
+    from nums_b200 import cuda_compute as cc
+    saved = cc.QR_SHIFTED_ENABLED
+    cc.QR_SHIFTED_ENABLED = False                  # the Householder kernel on the same block
+    try:
+        ran = _qr_r_checks(cuda_system, X, None, gram_tol=1e-13)
+        assert ran["householder"] == 1 and ran["gram3"] == 0, ran
+        Xi = _graded(40_000, 64, 1e9, seed=5)
+        ran = _qr_r_checks(cuda_system, Xi, None, gram_tol=1e-13)
+        assert ran["householder"] == 1, ran
+    finally:
+        cc.QR_SHIFTED_ENABLED = saved
     X32 = rng.standard_normal((50_000, 48)).astype(np.float32)     # float32 tall block: Householder kernel
     ran = _qr_r_checks(cuda_system, X32, 2e-5, gram_tol=2e-6)
     assert ran["householder"] == 1, ran
