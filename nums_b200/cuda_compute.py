@@ -1116,6 +1116,13 @@ def qr_r_ex(arr, gram=None):
     if not arr.is_contiguous():
         arr = _materialize(arr)
     m, n = arr.shape
+    if arr.dtype == torch.float32 and gram is None and QR_GRAM_ENABLED and n % 2 == 0 and 2 <= n <= QR_GRAM_MAX_COLS \
+            and m >= QR_GRAM_MIN_ASPECT * n and m >= 1024:
+        # tall float32 block: factor a float64 copy on the Gram path (one extra pass over the block instead of the
+        # Householder kernel's 128 dependent reflector steps per chunk) and round the result; the arithmetic is
+        # more accurate than the float32 LAPACK routine the reference calls
+        r64, kappa = qr_r_ex(_materialize(arr, torch.float64))
+        return _materialize(r64, torch.float32), kappa
     if gram is None and not _gram_path_ok(arr):
         return _householder_r(arr), None
     g0 = gram if gram is not None else _gram_of(arr)

@@ -912,8 +912,13 @@ def test_qr_rank_deficient_and_float32(cuda_system):
         assert ran["householder"] == 1, ran
     finally:
         cc.QR_SHIFTED_ENABLED = saved
-    X32 = rng.standard_normal((50_000, 48)).astype(np.float32)     # float32 tall block: Householder kernel
+    X32 = rng.standard_normal((50_000, 48)).astype(np.float32)     # float32 tall block: Gram path on a float64 copy
     ran = _qr_r_checks(cuda_system, X32, 2e-5, gram_tol=2e-6)
+    assert ran["gram"] == 1 and ran["householder"] == 0, ran
+    R32 = cuda_system.get(cuda_system.qr(cuda_system.put(X32), mode="r", axis=None, syskwargs={}))
+    assert R32.dtype == np.float32
+    X32w = rng.standard_normal((300, 48)).astype(np.float32)         # not tall enough: Householder kernel, float32 in and out
+    ran = _qr_r_checks(cuda_system, X32w, 2e-5, gram_tol=2e-6)
     assert ran["householder"] == 1, ran
     Xz = np.zeros((4096, 16))
     R = cuda_system.get(cuda_system.qr(cuda_system.put(Xz), mode="r", axis=None, syskwargs={}))
