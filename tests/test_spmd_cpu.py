@@ -147,6 +147,15 @@ def _worker(rank, world, port, results):
         Vb = app.array(vals, (125,)) + app.zero
         out["shuffle_vec"] = Vb[np.random.default_rng(8).permutation(1000)].get()
         out["shuffle_then_sum"] = app.sum(S0 + S0, axis=0).get()      # a pending chain consumed by another kernel
+        # a shuffle of a shuffle with nothing materialised in between, other block sizes, and a 3-D array along every axis
+        perm2 = np.random.default_rng(9).permutation(96)[:50]
+        out["shuffle_twice"] = Mb._advanced_single_array_subscript((perm0,), axis=0) \
+            ._advanced_single_array_subscript((perm2,), block_size=7, axis=0).get()
+        T3 = rng.standard_normal((12, 10, 9))
+        T3b = app.array(T3, (4, 5, 3)) + app.zero
+        out["_T3"] = T3
+        out["shuffle_3d"] = [T3b._advanced_single_array_subscript((np.random.default_rng(20 + ax).permutation(T3.shape[ax]),),
+                                                                  axis=ax).get() for ax in range(3)]
         out["stats"] = dict(system.stats)
         results[rank] = out
     finally:
@@ -197,6 +206,12 @@ def test_reference_host_layers_over_spmd(world):
         assert np.array_equal(r["shuffle1"], r["_M"][:, np.random.default_rng(6).permutation(40)[:25]])
         assert np.array_equal(r["shuffle_vec"], vals[np.random.default_rng(8).permutation(1000)])
         assert np.allclose(r["shuffle_then_sum"], 2 * r["_M"].sum(axis=0), rtol=1e-12, atol=1e-12)
+        assert np.array_equal(r["shuffle_twice"], r["_M"][np.random.default_rng(5).permutation(96)][
+            np.random.default_rng(9).permutation(96)[:50]])
+        for ax in range(3):
+            idx = [slice(None)] * 3
+            idx[ax] = np.random.default_rng(20 + ax).permutation(r["_T3"].shape[ax])
+            assert np.array_equal(r["shuffle_3d"][ax], r["_T3"][tuple(idx)])
         assert r["shuffle_homes"] == r["shuffle_owners"]                  # destination blocks live on their owners
         assert r["shuffle_whole_block_moves"] == 0                        # no source block travelled whole
         assert 0 < r["shuffle_row_bytes"] <= (96 * 40 + 96 * 25) * 8      # every row crossed the links at most once
