@@ -805,6 +805,9 @@ class ComputeCls(_ComputeImp):
         return _single_cta_factor(LIB.dll.nums_cholesky, upload(arr), "Matrix is not positive definite")
 
     def inv(self, arr):
+        known = getattr(arr, "_nums_inverse_t", None) if arr.__class__ is torch.Tensor else None
+        if known is not None:             # the R factor of a Gram-path qr: its inverse is (L^-1)^T, already computed
+            return _materialize(_transpose_view(known))
         return _single_cta_factor(LIB.dll.nums_inv, upload(arr), "Singular matrix")
 
     def svd(self, arr):
@@ -1050,6 +1053,9 @@ def _factor_gram(gram):
     bound = l1 * linf * i1 * iinf
     if failed != 0 or not np.isfinite(bound):
         return low, low_inv, upper, float("inf")
+    # R = L^T came with its inverse for free ((L^-1)^T): remember it on the tensor object, so that the inv(R) that
+    # indirect_tsqr asks for next (application.py:833, one 0.6 ms single-CTA Gauss-Jordan on every rank) is a transpose
+    upper._nums_inverse_t = low_inv
     return low, low_inv, upper, float(np.sqrt(bound))
 
 

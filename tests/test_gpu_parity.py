@@ -523,7 +523,11 @@ def test_gram_128_streaming_syrk(cuda_system, k):
     want = A.T @ A
     assert rel_fro(gram, want) <= GEMM_TOL
     assert np.array_equal(gram, gram.T)
-    # R through the public entry: qr(mode="r") on the Gram path
+    # R through the public entry: qr(mode="r") on the Gram path; its inverse comes with the factorization
+    Rdev = cuda_system.qr(t, mode="r", syskwargs={})
+    Rinv = cuda_system.get(cuda_system.inv(Rdev, syskwargs={}))
+    Rhost = cuda_system.get(Rdev)
+    assert np.linalg.norm(Rinv @ Rhost - np.eye(128)) <= 1e-10 and np.allclose(np.tril(Rinv, -1), 0)
     R = cuda_system.get(cuda_system.qr(t, mode="r", syskwargs={}))
     Rref = np.linalg.qr(A, mode="r")
     sg = np.sign(np.diag(R)) * np.sign(np.diag(Rref))
