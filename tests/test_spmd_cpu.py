@@ -40,6 +40,22 @@ def _app():
         pass
 
     local = OracleSystem()
+    # NumPy statements of the optional fused-LR kernels (cuda_compute.EXTRA_KERNELS), so that nums_b200.glms_fused
+    # and its grouping of row blocks by owner run over gloo as they do over NCCL
+    def lr_grad_hess(X, y, beta):
+        mu = 1.0 / (1.0 + np.exp(-(X @ beta)))
+        return np.concatenate([X.T @ (mu - y), (X.T @ ((mu * (1.0 - mu))[:, None] * X)).ravel()])
+
+    def lr_grad_hess_multi(*blocks):
+        beta = blocks[-1]
+        return sum(lr_grad_hess(blocks[i], blocks[i + 1], beta) for i in range(0, len(blocks) - 1, 2))
+
+    def newton_step(gh, beta):
+        d = beta.shape[0]
+        g, H = gh[:d], gh[d:].reshape(d, d)
+        return beta - np.linalg.inv(H) @ g, np.array([np.max(np.abs(g)), 0.0])
+    for fn in (lr_grad_hess, lr_grad_hess_multi, newton_step):
+        setattr(local.imp, fn.__name__, fn)
     system = OracleSpmdSystem(local, check=True)
     system.rng_cls = np_oracle.RNG
     system.init()
@@ -120,6 +136,14 @@ def _worker(rank, world, port, results):
         out["beta"] = beta.get()
         out["lr_moved_bytes"] = system.stats["moved_bytes"] - before["moved_bytes"]
         out["lr_all_reduces"] = system.stats["all_reduces"] - before["all_reduces"]
+        # the same fit through the drop-in on the fused kernels: one multi-block call per owner, one all-reduce / iteration
+        from nums_b200 import glms_fused
+        before = dict(system.stats)
+        executed = system.stats["executed"]
+        beta_f = glms_fused.newton(app, model, app.zeros((d,), (d,), dtype=np.float64), Xn, yn, app.scalar(1e-10), 6)
+        out["beta_fused"] = beta_f.get()
+        out["fused_moved_bytes"] = system.stats["moved_bytes"] - before["moved_bytes"]
+        out["fused_all_reduces"] = system.stats["all_reduces"] - before["all_reduces"]
 
         # ---- dynamic-size / carried-state kernels (description broadcast from the executing rank) --------------
         vals = rng.standard_normal(1000)
@@ -199,6 +223,8 @@ def test_reference_host_layers_over_spmd(world):
         assert rel_fro(r["Q"] @ r["R2"], T) < 1e-12 and rel_fro(r["Qd"] @ r["Rd"], T) < 1e-12
         assert np.linalg.norm(r["Q"].T @ r["Q"] - np.eye(16)) < 1e-10
         assert rel_fro(r["beta"], beta) < 1e-9
+        assert rel_fro(r["beta_fused"], beta) < 1e-9
+        assert r["fused_moved_bytes"] == 0 and 1 <= r["fused_all_reduces"] <= 7
         assert r["argmax"] == int(np.argmax(vals))
         assert len(r["where"]) == 1 and np.array_equal(r["where"][0], np.where(vals > 0.5)[0])
         assert np.array_equal(r["random"], results[0]["random"])          # same stream on every rank
